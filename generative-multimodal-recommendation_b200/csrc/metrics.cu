@@ -1,0 +1,163 @@
+// metrics.cu -- K4: hit matrix + Recall / NDCG / Precision / MAP prefix sums on the device.
+//
+// Replaces the pure-Python membership loop of GenMMRec/src/utils/topk_evaluator.py:107-112 and
+// the numpy kernels of GenMMRec/src/utils/metrics.py:12-105 (mean over users taken by the caller,
+// topk_evaluator.py:299-313).  Integer work (hits, cumulative hit counts) is bit-exact; the fp64
+// sums are accumulated in a FIXED order (warp tree -> warps in order -> blocks strided/tree), so the
+// result is run-to-run deterministic and within a few ulp of numpy's pairwise sum.
+#include <cmath>
+
+#include "common.cuh"
+#include "topk_select.cuh"
+
+namespace gmr {
+
+constexpr int kMU = 128;  // users per CTA (one thread each)
+constexpr int kKC = 32;   // top-K positions staged per pass
+
+__constant__ double c_discount[GMR_MAX_TOPK];  // 1 / log2(k + 2)
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    return v;
+}
+
+// block_sums layout: [4 * K][n_blocks]  (metric-major, then position, then block)
+__global__ void __launch_bounds__(kMU)
+    hits_metrics_kernel(const int32_t* __restrict__ topk, const int64_t* __restrict__ gt_rowptr,
+                        const int32_t* __restrict__ gt_items, int32_t U, int32_t K, uint8_t* __restrict__ hit,
+                        double* __restrict__ block_sums)
+{
+    __shared__ int32_t tile[kMU][kKC + 1];
+    __shared__ double wsum[kMU / 32][4][kKC];
+
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int64_t u0 = (int64_t)blockIdx.x * kMU;
+    const int64_t u = u0 + t;
+    const bool valid = u < U;
+    int64_t lo = 0, hi = 0;
+    if (valid) {
+        lo = gt_rowptr[u];
+        hi = gt_rowptr[u + 1];
+    }
+    const double n = (double)(hi - lo);
+    const int lim = (int)min((int64_t)K, hi - lo);
+    double c = 0.0, dcg = 0.0, idcg = 0.0, sp = 0.0;
+
+    for (int k0 = 0; k0 < K; k0 += kKC) {
+        const int kc = min(kKC, K - k0);
+        __syncthreads();
+        // coalesced stage-in of topk[u0 : u0+128, k0 : k0+kc]
+        for (int idx = t; idx < kMU * kc; idx += kMU) {
+            const int r = idx / kc, k = idx - r * kc;
+            tile[r][k] = (u0 + r < U) ? topk[(u0 + r) * K + k0 + k] : -1;
+        }
+        __syncthreads();
+        for (int k = 0; k < kc; ++k) {
+            const int pos = k0 + k;
+            int h = 0;
+            if (valid) h = sorted_contains(gt_items, lo, hi, tile[t][k]) ? 1 : 0;
+            tile[t][k] = h;
+            double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+            if (valid) {
+                const double disc = c_discount[pos];
+                c += (double)h;
+                dcg += (double)h * disc;
+                if (pos < lim) idcg += disc;
+                sp += (double)h * (c / (double)(pos + 1));
+                v0 = c / n;
+                v1 = dcg / idcg;
+                v2 = c / (double)(pos + 1);
+                v3 = sp / (double)min(pos + 1, lim);
+            }
+            v0 = warp_sum(v0);
+            v1 = warp_sum(v1);
+            v2 = warp_sum(v2);
+            v3 = warp_sum(v3);
+            if (lane == 0) {
+                wsum[warp][0][k] = v0;
+                wsum[warp][1][k] = v1;
+                wsum[warp][2][k] = v2;
+                wsum[warp][3][k] = v3;
+            }
+        }
+        __syncthreads();
+        if (hit != nullptr) {
+            for (int idx = t; idx < kMU * kc; idx += kMU) {
+                const int r = idx / kc, k = idx - r * kc;
+                if (u0 + r < U) hit[(u0 + r) * K + k0 + k] = (uint8_t)tile[r][k];
+            }
+        }
+        for (int idx = t; idx < 4 * kc; idx += kMU) {
+            const int m = idx / kc, k = idx - m * kc;
+            double s = wsum[0][m][k];
+#pragma unroll
+            for (int w = 1; w < kMU / 32; ++w) s += wsum[w][m][k];
+            block_sums[((int64_t)m * K + k0 + k) * gridDim.x + blockIdx.x] = s;
+        }
+    }
+}
+
+// one CTA per (metric, position): strided fixed-order partial sums, then a shared-memory tree
+__global__ void __launch_bounds__(256) metrics_final_kernel(const double* __restrict__ block_sums, int32_t n_blocks,
+                                                            double* __restrict__ sums)
+{
+    __shared__ double red[256];
+    const double* src = block_sums + (int64_t)blockIdx.x * n_blocks;
+    double s = 0.0;
+    for (int b = threadIdx.x; b < n_blocks; b += 256) s += src[b];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sums[blockIdx.x] = red[0];
+}
+
+static bool g_discount_ready = false;
+
+}  // namespace gmr
+
+extern "C" int64_t gmr_hits_metrics_workspace_bytes(int32_t U, int32_t K)
+{
+    if (U <= 0 || K <= 0) return 0;
+    const int64_t nb = ((int64_t)U + gmr::kMU - 1) / gmr::kMU;
+    return gmr::align_up(nb * 4 * K * (int64_t)sizeof(double), 256);
+}
+
+extern "C" int gmr_hits_metrics(const int32_t* topk, const int64_t* gt_rowptr, const int32_t* gt_items, int32_t U,
+                                int32_t K, uint8_t* hit, double* sums, void* workspace, int64_t workspace_bytes,
+                                void* stream)
+{
+    GMR_REQUIRE(K >= 1 && K <= GMR_MAX_TOPK, "gmr_hits_metrics: K=%d outside [1, %d]", K, GMR_MAX_TOPK);
+    GMR_REQUIRE(U >= 0, "gmr_hits_metrics: negative user count");
+    GMR_REQUIRE(sums != nullptr, "gmr_hits_metrics: null sums");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (U == 0) {
+        GMR_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 4 * K, st));
+        return GMR_OK;
+    }
+    GMR_REQUIRE(topk && gt_rowptr && gt_items, "gmr_hits_metrics: null operand");
+    const int64_t need = gmr_hits_metrics_workspace_bytes(U, K);
+    if (workspace == nullptr || workspace_bytes < need) {
+        gmr::set_error("gmr_hits_metrics: workspace of %lld bytes required, %lld given", (long long)need,
+                       (long long)workspace_bytes);
+        return GMR_ERR_WORKSPACE;
+    }
+    if (!gmr::g_discount_ready) {
+        // same expression as GenMMRec/src/utils/metrics.py:53,59: 1.0 / np.log2(rank + 1), rank = k + 1
+        double h[GMR_MAX_TOPK];
+        for (int k = 0; k < GMR_MAX_TOPK; ++k) h[k] = 1.0 / std::log2((double)k + 2.0);
+        GMR_CHECK_CUDA(cudaMemcpyToSymbol(gmr::c_discount, h, sizeof(h)));
+        gmr::g_discount_ready = true;
+    }
+    const int nb = (int)(((int64_t)U + gmr::kMU - 1) / gmr::kMU);
+    gmr::hits_metrics_kernel<<<nb, gmr::kMU, 0, st>>>(topk, gt_rowptr, gt_items, U, K, hit, (double*)workspace);
+    GMR_LAUNCH_CHECK();
+    gmr::metrics_final_kernel<<<4 * K, 256, 0, st>>>((const double*)workspace, nb, sums);
+    GMR_LAUNCH_CHECK();
+    return GMR_OK;
+}

@@ -1,0 +1,488 @@
+// spmm.cu -- K1: CSR SpMM  Y = alpha * A * X + beta * Y  (fp32, sm_100a)
+//
+// Replaces torch.sparse.mm / torch.spmm(A_coo, X) at the reference call sites listed in
+// include/gmr.h (GenMMRec/src/models/diffmm.py:136-152,284-285 and siblings).
+//
+// Schedule
+//   * the plan cuts every row into "virtual rows" of at most `chunk` nonzeros; one WARP owns one
+//     virtual row, so no warp ever walks a power-law row alone (item rows of the 1M-user shape
+//     reach 10^5..10^6 nonzeros).  Virtual rows are contiguous in nnz space, so they are described
+//     by one CSR-like pointer array (vptr) plus a destination per virtual row.
+//   * whole rows are written straight to Y; chunks of split rows write fp32 partial sums to the
+//     workspace and a second kernel adds them up in slot order (fixed order => deterministic).
+//   * inside a warp the (col, val) pairs of up to 32 nonzeros are loaded coalesced, staged in
+//     shared memory, and consumed LANES lanes per nonzero: D = 64 uses 16 lanes x 128-bit per
+//     gathered embedding row, i.e. two nonzeros per warp step; loads are issued UNROLL steps ahead
+//     of the FMAs to keep >= 8 independent 128-bit gathers in flight per warp.
+//   * the CSR stream is read with L1::no_allocate + L2::evict_first, gathered rows with
+//     L2::evict_last: the only operand with reuse keeps the 126 MB L2.
+//
+// HBM-bound: algorithmic bytes = nnz*8 + (n_rows+1)*4 + n_cols*D*4 + n_rows*D*4.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+struct gmr_spmm_plan {
+    int64_t n_rows = 0, n_cols = 0, nnz = 0;
+    int32_t chunk = 0;
+    int64_t n_vrows = 0;       // virtual rows (chunks)
+    int64_t n_split_rows = 0;  // rows cut into more than one chunk
+    int64_t n_slots = 0;       // partial-sum slots = chunks of split rows
+    int32_t max_slots_per_row = 0;
+    // device arrays (null when the plan is the identity: no row longer than `chunk`)
+    int32_t* d_vptr = nullptr;         // [n_vrows + 1]
+    int32_t* d_vrow = nullptr;         // [n_vrows]  row id, or -1 - slot for a chunk of a split row
+    int32_t* d_split_row = nullptr;    // [n_split_rows]
+    int32_t* d_split_first = nullptr;  // [n_split_rows + 1] first slot of each split row
+};
+
+namespace gmr {
+
+constexpr int kWarps = 8;  // warps per CTA (256 threads)
+
+template <typename Vec>
+struct VecOps;
+template <>
+struct VecOps<float4> {
+    static __device__ __forceinline__ float4 zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+    static __device__ __forceinline__ float4 gather(const float4* p, uint64_t pol) { return ld_gather_f4(p, pol); }
+    static __device__ __forceinline__ void fma(float4& a, float w, const float4& x)
+    {
+        a.x = fmaf(w, x.x, a.x);
+        a.y = fmaf(w, x.y, a.y);
+        a.z = fmaf(w, x.z, a.z);
+        a.w = fmaf(w, x.w, a.w);
+    }
+    static __device__ __forceinline__ float4 xor_add(float4 a, int m)
+    {
+        a.x += __shfl_xor_sync(0xffffffffu, a.x, m);
+        a.y += __shfl_xor_sync(0xffffffffu, a.y, m);
+        a.z += __shfl_xor_sync(0xffffffffu, a.z, m);
+        a.w += __shfl_xor_sync(0xffffffffu, a.w, m);
+        return a;
+    }
+    static __device__ __forceinline__ float4 axpby(float alpha, const float4& a, float beta, const float4& y)
+    {
+        return make_float4(fmaf(alpha, a.x, beta * y.x), fmaf(alpha, a.y, beta * y.y), fmaf(alpha, a.z, beta * y.z),
+                           fmaf(alpha, a.w, beta * y.w));
+    }
+    static __device__ __forceinline__ float4 scale(float alpha, const float4& a)
+    {
+        return make_float4(alpha * a.x, alpha * a.y, alpha * a.z, alpha * a.w);
+    }
+    static __device__ __forceinline__ float4 add(const float4& a, const float4& b)
+    {
+        return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    }
+};
+template <>
+struct VecOps<float> {
+    static __device__ __forceinline__ float zero() { return 0.f; }
+    static __device__ __forceinline__ float gather(const float* p, uint64_t pol) { return ld_gather_f1(p, pol); }
+    static __device__ __forceinline__ void fma(float& a, float w, const float& x) { a = fmaf(w, x, a); }
+    static __device__ __forceinline__ float xor_add(float a, int m) { return a + __shfl_xor_sync(0xffffffffu, a, m); }
+    static __device__ __forceinline__ float axpby(float alpha, const float& a, float beta, const float& y)
+    {
+        return fmaf(alpha, a, beta * y);
+    }
+    static __device__ __forceinline__ float scale(float alpha, const float& a) { return alpha * a; }
+    static __device__ __forceinline__ float add(const float& a, const float& b) { return a + b; }
+};
+
+struct PushArgs {
+    float* const* y_peers;
+    int32_t n_peers;
+    int64_t row_offset;
+};
+
+// One warp per virtual row.  Vec = float4 (D % 4 == 0, aligned) or float.  DV = row length in Vec.
+template <typename Vec, int LANES, int ITER, bool IDENT, bool PUSH>
+__global__ void __launch_bounds__(kWarps * 32)
+    spmm_vrow_kernel(const int32_t* __restrict__ vptr, const int32_t* __restrict__ vrow,
+                     const int32_t* __restrict__ col, const float* __restrict__ val, const float* __restrict__ X,
+                     int64_t ldx, float* __restrict__ Y, int64_t ldy, float* __restrict__ partial, int32_t DV,
+                     int64_t n_vrows, float alpha, float beta, PushArgs push)
+{
+    using Ops = VecOps<Vec>;
+    constexpr int VEC = sizeof(Vec) / 4;
+    constexpr int NPS = 32 / LANES;              // nonzeros consumed per warp step
+    constexpr int UNROLL = (ITER >= 2) ? 2 : 4;  // steps whose gathers are issued back to back
+    static_assert(32 % (NPS * UNROLL) == 0, "batch must tile the 32-entry stage");
+
+    __shared__ int2 stage[kWarps][32];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t v = (int64_t)blockIdx.x * kWarps + warp;
+    if (v >= n_vrows) return;  // whole warp leaves together; only __syncwarp below
+
+    const int begin = vptr[v], end = vptr[v + 1];
+    const int dst = IDENT ? (int)v : vrow[v];
+    const int sub = lane % LANES, grp = lane / LANES;
+    const int vcol0 = blockIdx.y * (LANES * ITER) + sub;  // this lane's first Vec column
+
+    const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+    Vec acc[ITER];
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) acc[it] = Ops::zero();
+
+    for (int base = begin; base < end; base += 32) {
+        const int n = min(32, end - base);
+        int c = 0;
+        float w = 0.f;
+        if (lane < n) {
+            c = ld_stream_s32(col + base + lane, pol_stream);
+            w = ld_stream_f32(val + base + lane, pol_stream);
+        }
+        __syncwarp();
+        stage[warp][lane] = make_int2(c, __float_as_int(w));
+        __syncwarp();
+        for (int j = 0; j < n; j += NPS * UNROLL) {
+            Vec xv[UNROLL][ITER];
+            float wq[UNROLL];
+#pragma unroll
+            for (int q = 0; q < UNROLL; ++q) {
+                const int e = j + q * NPS + grp;
+                const int2 cw = stage[warp][e];
+                const bool ok = e < n;
+                wq[q] = ok ? __int_as_float(cw.y) : 0.f;
+                const Vec* xr = reinterpret_cast<const Vec*>(X + (int64_t)cw.x * ldx);
+#pragma unroll
+                for (int it = 0; it < ITER; ++it) {
+                    const int vc = vcol0 + it * LANES;
+                    xv[q][it] = (ok && vc < DV) ? Ops::gather(xr + vc, pol_keep) : Ops::zero();
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < UNROLL; ++q)
+#pragma unroll
+                for (int it = 0; it < ITER; ++it) Ops::fma(acc[it], wq[q], xv[q][it]);
+        }
+    }
+
+    if (NPS == 2) {
+#pragma unroll
+        for (int it = 0; it < ITER; ++it) acc[it] = Ops::xor_add(acc[it], 16);
+    }
+    if (grp != 0) return;
+
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+        const int vc = vcol0 + it * LANES;
+        if (vc >= DV) continue;
+        if (!IDENT && dst < 0) {
+            // chunk of a split row: raw partial sum, reduced later in slot order
+            Vec* p = reinterpret_cast<Vec*>(partial + (int64_t)(-1 - dst) * ((int64_t)DV * VEC)) + vc;
+            *p = acc[it];
+        } else if (PUSH) {
+            const Vec out = Ops::scale(alpha, acc[it]);
+            for (int p = 0; p < push.n_peers; ++p) {
+                Vec* y = reinterpret_cast<Vec*>(push.y_peers[p] + (push.row_offset + dst) * ldy) + vc;
+                *y = out;
+            }
+        } else {
+            Vec* y = reinterpret_cast<Vec*>(Y + (int64_t)dst * ldy) + vc;
+            *y = (beta == 0.f) ? Ops::scale(alpha, acc[it]) : Ops::axpby(alpha, acc[it], beta, *y);
+        }
+    }
+}
+
+// One CTA per split row: warp w sums the slots of its fixed sub-range in order, the eight warp
+// sums are then added in warp order.  Fixed order => deterministic.
+template <typename Vec, bool PUSH>
+__global__ void __launch_bounds__(kWarps * 32)
+    spmm_reduce_kernel(const int32_t* __restrict__ split_row, const int32_t* __restrict__ split_first,
+                       const float* __restrict__ partial, float* __restrict__ Y, int64_t ldy, int32_t DV,
+                       float alpha, float beta, PushArgs push)
+{
+    using Ops = VecOps<Vec>;
+    constexpr int VEC = sizeof(Vec) / 4;
+    extern __shared__ float4 red_smem[];  // [kWarps][DV] Vec
+    Vec* red = reinterpret_cast<Vec*>(red_smem);
+
+    const int s = blockIdx.x;
+    const int row = split_row[s];
+    const int first = split_first[s], n = split_first[s + 1] - first;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per = (n + kWarps - 1) / kWarps;
+    const int lo = min(n, warp * per), hi = min(n, lo + per);
+    const Vec* base = reinterpret_cast<const Vec*>(partial + (int64_t)first * ((int64_t)DV * VEC));
+
+    for (int vc = lane; vc < DV; vc += 32) {
+        Vec a = Ops::zero();
+        for (int k = lo; k < hi; ++k) a = Ops::add(a, base[(int64_t)k * DV + vc]);
+        red[warp * DV + vc] = a;
+    }
+    __syncthreads();
+    for (int vc = threadIdx.x; vc < DV; vc += kWarps * 32) {
+        Vec a = red[vc];
+#pragma unroll
+        for (int w = 1; w < kWarps; ++w) a = Ops::add(a, red[w * DV + vc]);
+        if (PUSH) {
+            const Vec out = Ops::scale(alpha, a);
+            for (int p = 0; p < push.n_peers; ++p)
+                reinterpret_cast<Vec*>(push.y_peers[p] + (push.row_offset + row) * ldy)[vc] = out;
+        } else {
+            Vec* y = reinterpret_cast<Vec*>(Y + (int64_t)row * ldy) + vc;
+            *y = (beta == 0.f) ? Ops::scale(alpha, a) : Ops::axpby(alpha, a, beta, *y);
+        }
+    }
+}
+
+template <typename Vec, int LANES, int ITER, bool PUSH>
+static int launch_vrow(const gmr_spmm_plan* plan, const int32_t* rowptr, const int32_t* col, const float* val,
+                       const float* X, int64_t ldx, float* Y, int64_t ldy, float* partial, int32_t DV, float alpha,
+                       float beta, PushArgs push, cudaStream_t st)
+{
+    const bool ident = plan->d_vptr == nullptr;
+    const int64_t nv = plan->n_vrows;
+    if (nv == 0) return GMR_OK;
+    dim3 grid((unsigned)((nv + kWarps - 1) / kWarps), (unsigned)((DV + LANES * ITER - 1) / (LANES * ITER)));
+    dim3 block(kWarps * 32);
+    if (ident)
+        spmm_vrow_kernel<Vec, LANES, ITER, true, PUSH><<<grid, block, 0, st>>>(rowptr, nullptr, col, val, X, ldx, Y, ldy,
+                                                                             partial, DV, nv, alpha, beta, push);
+    else
+        spmm_vrow_kernel<Vec, LANES, ITER, false, PUSH><<<grid, block, 0, st>>>(plan->d_vptr, plan->d_vrow, col, val, X,
+                                                                              ldx, Y, ldy, partial, DV, nv, alpha,
+                                                                              beta, push);
+    GMR_LAUNCH_CHECK();
+    return GMR_OK;
+}
+
+template <typename Vec, bool PUSH>
+static int dispatch(const gmr_spmm_plan* plan, const int32_t* rowptr, const int32_t* col, const float* val,
+                    const float* X, int64_t ldx, float* Y, int64_t ldy, float* partial, int32_t D, float alpha,
+                    float beta, PushArgs push, cudaStream_t st)
+{
+    constexpr int VEC = sizeof(Vec) / 4;
+    const int32_t DV = D / VEC;
+    int rc;
+    if (DV <= 16)
+        rc = launch_vrow<Vec, 16, 1, PUSH>(plan, rowptr, col, val, X, ldx, Y, ldy, partial, DV, alpha, beta, push, st);
+    else if (DV <= 32)
+        rc = launch_vrow<Vec, 32, 1, PUSH>(plan, rowptr, col, val, X, ldx, Y, ldy, partial, DV, alpha, beta, push, st);
+    else if (DV <= 64)
+        rc = launch_vrow<Vec, 32, 2, PUSH>(plan, rowptr, col, val, X, ldx, Y, ldy, partial, DV, alpha, beta, push, st);
+    else
+        rc = launch_vrow<Vec, 32, 4, PUSH>(plan, rowptr, col, val, X, ldx, Y, ldy, partial, DV, alpha, beta, push, st);
+    if (rc != GMR_OK) return rc;
+    if (plan->n_split_rows > 0) {
+        const size_t smem = (size_t)kWarps * DV * sizeof(Vec);
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(spmm_reduce_kernel<Vec, PUSH>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) {
+                set_error("row width D=%d too large for the split-row reduction (%zu B shared)", D, smem);
+                return GMR_ERR_UNSUPPORTED;
+            }
+        }
+        spmm_reduce_kernel<Vec, PUSH><<<(unsigned)plan->n_split_rows, kWarps * 32, smem, st>>>(
+            plan->d_split_row, plan->d_split_first, partial, Y, ldy, DV, alpha, beta, push);
+        GMR_LAUNCH_CHECK();
+    }
+    return GMR_OK;
+}
+
+static int spmm_common(const gmr_spmm_plan* plan, const int32_t* rowptr, const int32_t* col, const float* val,
+                       const float* X, int64_t ldx, float* Y, int64_t ldy, int32_t D, float alpha, float beta,
+                       PushArgs push, bool is_push, void* workspace, int64_t workspace_bytes, void* stream)
+{
+    GMR_REQUIRE(plan != nullptr, "gmr_spmm: plan is null");
+    GMR_REQUIRE(D >= 1, "gmr_spmm: D must be >= 1 (got %d)", D);
+    GMR_REQUIRE(ldx >= D && ldy >= D, "gmr_spmm: leading dimensions (%lld, %lld) smaller than D=%d", (long long)ldx,
+                (long long)ldy, D);
+    if (plan->n_rows == 0) return GMR_OK;
+    GMR_REQUIRE(rowptr && X && (Y || is_push), "gmr_spmm: null operand");
+    GMR_REQUIRE(plan->nnz == 0 || (col && val), "gmr_spmm: null col/val with nnz > 0");
+    const int64_t need = gmr_spmm_workspace_bytes(plan, D);
+    if (need > 0 && (workspace == nullptr || workspace_bytes < need)) {
+        set_error("gmr_spmm: workspace of %lld bytes required, %lld given", (long long)need, (long long)workspace_bytes);
+        return GMR_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    float* partial = (float*)workspace;
+    bool vec4 = (D % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && ((uintptr_t)X % 16 == 0);
+    if (!is_push) vec4 = vec4 && ((uintptr_t)Y % 16 == 0);
+    if (is_push) {
+        if (vec4) return dispatch<float4, true>(plan, rowptr, col, val, X, ldx, Y, ldy, partial, D, alpha, beta, push, st);
+        return dispatch<float, true>(plan, rowptr, col, val, X, ldx, Y, ldy, partial, D, alpha, beta, push, st);
+    }
+    if (vec4) return dispatch<float4, false>(plan, rowptr, col, val, X, ldx, Y, ldy, partial, D, alpha, beta, push, st);
+    return dispatch<float, false>(plan, rowptr, col, val, X, ldx, Y, ldy, partial, D, alpha, beta, push, st);
+}
+
+// ---- row-wise glue ---------------------------------------------------------------------------
+// out = a*x + b*y + c * z / max(||z||_2, eps); one warp per row.
+__global__ void __launch_bounds__(256)
+    rows_axpby_norm_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ y, int64_t ldy,
+                           const float* __restrict__ z, int64_t ldz, float* __restrict__ out, int64_t ldo,
+                           int64_t n_rows, int32_t D, float a, float b, float c, float eps)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n_rows) return;
+    float inv = 0.f;
+    if (z != nullptr) {
+        float ss = 0.f;
+        for (int d = lane; d < D; d += 32) {
+            const float t = z[r * ldz + d];
+            ss = fmaf(t, t, ss);
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, m);
+        inv = c / fmaxf(sqrtf(ss), eps);
+    }
+    for (int d = lane; d < D; d += 32) {
+        float o = a * x[r * ldx + d];
+        if (y != nullptr) o = fmaf(b, y[r * ldy + d], o);
+        if (z != nullptr) o = fmaf(inv, z[r * ldz + d], o);
+        out[r * ldo + d] = o;
+    }
+}
+
+}  // namespace gmr
+
+// ---- C ABI -------------------------------------------------------------------------------------
+
+extern "C" int gmr_spmm_plan_create(gmr_spmm_plan_t** out, const int32_t* rowptr, int64_t n_rows, int64_t n_cols,
+                                    int32_t chunk_nnz, void* stream)
+{
+    GMR_REQUIRE(out != nullptr, "gmr_spmm_plan_create: null output handle");
+    *out = nullptr;
+    GMR_REQUIRE(n_rows >= 0 && n_cols >= 0, "gmr_spmm_plan_create: negative shape");
+    GMR_REQUIRE(n_rows < (int64_t)0x7fffffff && n_cols < (int64_t)0x7fffffff, "gmr_spmm_plan_create: shape exceeds int32");
+    GMR_REQUIRE(n_rows == 0 || rowptr != nullptr, "gmr_spmm_plan_create: null rowptr");
+    GMR_REQUIRE(chunk_nnz >= 0, "gmr_spmm_plan_create: negative chunk");
+    const int32_t chunk = chunk_nnz == 0 ? 256 : std::max(32, (chunk_nnz + 31) / 32 * 32);
+    cudaStream_t st = (cudaStream_t)stream;
+
+    std::vector<int32_t> h(n_rows + 1, 0);
+    if (n_rows > 0) {
+        GMR_CHECK_CUDA(cudaMemcpyAsync(h.data(), rowptr, sizeof(int32_t) * (n_rows + 1), cudaMemcpyDeviceToHost, st));
+        GMR_CHECK_CUDA(cudaStreamSynchronize(st));
+    }
+    GMR_REQUIRE(h[0] == 0, "gmr_spmm_plan_create: rowptr[0] must be 0 (got %d)", h[0]);
+    for (int64_t r = 0; r < n_rows; ++r)
+        GMR_REQUIRE(h[r + 1] >= h[r], "gmr_spmm_plan_create: rowptr not monotone at row %lld", (long long)r);
+
+    auto* p = new gmr_spmm_plan();
+    p->n_rows = n_rows;
+    p->n_cols = n_cols;
+    p->nnz = n_rows > 0 ? h[n_rows] : 0;
+    p->chunk = chunk;
+    int64_t n_split = 0, n_extra = 0;
+    for (int64_t r = 0; r < n_rows; ++r) {
+        const int32_t len = h[r + 1] - h[r];
+        if (len > chunk) {
+            ++n_split;
+            n_extra += (len + chunk - 1) / chunk - 1;
+        }
+    }
+    p->n_split_rows = n_split;
+    p->n_vrows = n_rows + n_extra;
+    if (n_split > 0) {
+        std::vector<int32_t> vptr, vrow, srow, sfirst;
+        vptr.reserve(p->n_vrows + 1);
+        vrow.reserve(p->n_vrows);
+        vptr.push_back(0);
+        int32_t slot = 0;
+        for (int64_t r = 0; r < n_rows; ++r) {
+            const int32_t b = h[r], e = h[r + 1], len = e - b;
+            if (len <= chunk) {
+                vptr.push_back(e);
+                vrow.push_back((int32_t)r);
+            } else {
+                const int32_t k = (len + chunk - 1) / chunk;
+                srow.push_back((int32_t)r);
+                sfirst.push_back(slot);
+                p->max_slots_per_row = std::max(p->max_slots_per_row, k);
+                for (int32_t c = 0; c < k; ++c) {
+                    vptr.push_back(std::min(b + (c + 1) * chunk, e));
+                    vrow.push_back(-1 - slot);
+                    ++slot;
+                }
+            }
+        }
+        sfirst.push_back(slot);
+        p->n_slots = slot;
+        auto upload = [&](int32_t** d, const std::vector<int32_t>& v) -> cudaError_t {
+            cudaError_t e = cudaMalloc((void**)d, sizeof(int32_t) * std::max<size_t>(1, v.size()));
+            if (e != cudaSuccess) return e;
+            return cudaMemcpyAsync(*d, v.data(), sizeof(int32_t) * v.size(), cudaMemcpyHostToDevice, st);
+        };
+        cudaError_t e = upload(&p->d_vptr, vptr);
+        if (e == cudaSuccess) e = upload(&p->d_vrow, vrow);
+        if (e == cudaSuccess) e = upload(&p->d_split_row, srow);
+        if (e == cudaSuccess) e = upload(&p->d_split_first, sfirst);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // host vectors die at scope exit
+        if (e != cudaSuccess) {
+            gmr::set_error("gmr_spmm_plan_create: %s", cudaGetErrorString(e));
+            gmr_spmm_plan_destroy(p);
+            return GMR_ERR_CUDA;
+        }
+    }
+    *out = p;
+    return GMR_OK;
+}
+
+extern "C" int gmr_spmm_plan_destroy(gmr_spmm_plan_t* p)
+{
+    if (p == nullptr) return GMR_OK;
+    cudaFree(p->d_vptr);
+    cudaFree(p->d_vrow);
+    cudaFree(p->d_split_row);
+    cudaFree(p->d_split_first);
+    delete p;
+    return GMR_OK;
+}
+
+extern "C" int gmr_spmm_plan_stats(const gmr_spmm_plan_t* p, int64_t* n_chunks, int64_t* n_split_rows, int64_t* nnz)
+{
+    GMR_REQUIRE(p != nullptr, "gmr_spmm_plan_stats: null plan");
+    if (n_chunks) *n_chunks = p->n_vrows;
+    if (n_split_rows) *n_split_rows = p->n_split_rows;
+    if (nnz) *nnz = p->nnz;
+    return GMR_OK;
+}
+
+extern "C" int64_t gmr_spmm_workspace_bytes(const gmr_spmm_plan_t* p, int32_t D)
+{
+    if (p == nullptr || D < 1) return 0;
+    return gmr::align_up(p->n_slots * (int64_t)D * (int64_t)sizeof(float), 256);
+}
+
+extern "C" int gmr_spmm_csr_f32(const gmr_spmm_plan_t* plan, const int32_t* rowptr, const int32_t* col,
+                                const float* val, const float* X, int64_t ldx, float* Y, int64_t ldy, int32_t D,
+                                float alpha, float beta, void* workspace, int64_t workspace_bytes, void* stream)
+{
+    gmr::PushArgs push{nullptr, 0, 0};
+    return gmr::spmm_common(plan, rowptr, col, val, X, ldx, Y, ldy, D, alpha, beta, push, false, workspace,
+                            workspace_bytes, stream);
+}
+
+extern "C" int gmr_spmm_csr_f32_push(const gmr_spmm_plan_t* plan, const int32_t* rowptr, const int32_t* col,
+                                     const float* val, const float* X, int64_t ldx, float* const* y_peers,
+                                     int32_t n_peers, int64_t row_offset, int64_t ldy, int32_t D, float alpha,
+                                     void* workspace, int64_t workspace_bytes, void* stream)
+{
+    GMR_REQUIRE(y_peers != nullptr && n_peers >= 1, "gmr_spmm_csr_f32_push: need at least one destination");
+    GMR_REQUIRE(row_offset >= 0, "gmr_spmm_csr_f32_push: negative row offset");
+    gmr::PushArgs push{y_peers, n_peers, row_offset};
+    return gmr::spmm_common(plan, rowptr, col, val, X, ldx, nullptr, ldy, D, alpha, 0.f, push, true, workspace,
+                            workspace_bytes, stream);
+}
+
+extern "C" int gmr_rows_axpby_norm_f32(const float* x, int64_t ldx, const float* y, int64_t ldy, const float* z,
+                                       int64_t ldz, float* out, int64_t ldo, int64_t n_rows, int32_t D, float a,
+                                       float b, float c, float eps, void* stream)
+{
+    GMR_REQUIRE(x != nullptr && out != nullptr, "gmr_rows_axpby_norm_f32: null x/out");
+    GMR_REQUIRE(D >= 1 && n_rows >= 0, "gmr_rows_axpby_norm_f32: bad shape");
+    if (n_rows == 0) return GMR_OK;
+    const int wpb = 8;
+    gmr::rows_axpby_norm_kernel<<<(unsigned)((n_rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+        x, ldx, y, ldy, z, ldz, out, ldo, n_rows, D, a, b, c, eps);
+    GMR_LAUNCH_CHECK();
+    return GMR_OK;
+}

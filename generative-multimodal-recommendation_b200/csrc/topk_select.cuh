@@ -1,0 +1,132 @@
+// topk_select.cuh -- per-row running top-K used by the fused scoring kernels (K2).
+//
+// Every candidate is one 64-bit key: (order-preserving fp32 score) << 32 | (0xFFFFFFFF - item id),
+// so "larger key" == "higher score, then lower item id" -- the total order of the oracle
+// (oracle/gmr_oracle.c: better()).  A row owns CAP = 32 * NPL key slots in the workspace:
+// slots [0, KP) hold the current best KP = CAP / 4 keys (sorted, after a compaction), the rest is
+// an append-only pending region.  A score is appended only if it beats the row's threshold (the
+// key at position `kth` after the last compaction), so once the threshold is warm almost nothing
+// is appended.  A compaction is a warp-level bitonic sort of the CAP keys held NPL per lane.
+#pragma once
+
+#include <stdint.h>
+
+namespace gmr {
+
+__device__ __forceinline__ uint32_t f32_to_ordered(float f)
+{
+    const uint32_t u = __float_as_uint(f + 0.0f);  // -0.0f -> +0.0f so that equal floats give equal keys
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_f32(uint32_t o)
+{
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+__device__ __forceinline__ uint64_t make_key(float score, int32_t id)
+{
+    return ((uint64_t)f32_to_ordered(score) << 32) | (uint64_t)(0xFFFFFFFFu - (uint32_t)id);
+}
+__device__ __forceinline__ int32_t key_id(uint64_t k) { return (int32_t)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFu)); }
+__device__ __forceinline__ float key_score(uint64_t k) { return ordered_to_f32((uint32_t)(k >> 32)); }
+
+// Sort 32 * NPL keys held as k[r] = element (r * 32 + lane), descending (element 0 = largest).
+template <int NPL>
+__device__ __forceinline__ void warp_bitonic_sort_desc(uint64_t (&k)[NPL], int lane)
+{
+    constexpr int N = 32 * NPL;
+#pragma unroll
+    for (int size = 2; size <= N; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride < 32) {
+#pragma unroll
+                for (int r = 0; r < NPL; ++r) {
+                    const int i = r * 32 + lane;
+                    const uint64_t other = __shfl_xor_sync(0xffffffffu, k[r], stride);
+                    const bool desc = (i & size) == 0;
+                    const bool lower = (lane & stride) == 0;
+                    const bool take_max = (lower == desc);
+                    const uint64_t mx = k[r] > other ? k[r] : other;
+                    const uint64_t mn = k[r] > other ? other : k[r];
+                    k[r] = take_max ? mx : mn;
+                }
+            } else {
+                constexpr int dummy = 0;
+                (void)dummy;
+                const int rs = stride >> 5;
+#pragma unroll
+                for (int r = 0; r < NPL; ++r) {
+                    if ((r & rs) == 0) {
+                        const int r2 = r | rs;
+                        const int i = r * 32 + lane;
+                        const bool desc = (i & size) == 0;
+                        const uint64_t a = k[r], b = k[r2];
+                        const uint64_t mx = a > b ? a : b;
+                        const uint64_t mn = a > b ? b : a;
+                        k[r] = desc ? mx : mn;
+                        k[r2] = desc ? mn : mx;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Per-row selection state kept in shared memory by the calling CTA.
+struct RowState {
+    int cnt;           // valid keys in the row's slots (may run past CAP while appends are failing)
+    float thr_score;   // score part of the threshold (fast reject)
+    uint64_t thr_key;  // full threshold key: only keys > thr_key can still enter the top-K
+};
+
+// Warp-cooperative compaction of one row: keep the best KP keys (sorted) in slots [0, KP),
+// refresh the threshold from position `kth` (0-based).  All 32 lanes must call.
+template <int NPL>
+__device__ __noinline__ void compact_row(uint64_t* __restrict__ slots, RowState* st, int kth, int lane)
+{
+    constexpr int CAP = 32 * NPL;
+    constexpr int KP = CAP / 4;
+    static_assert(NPL % 4 == 0, "KP must be a multiple of 32 keys");
+    const int cnt = min(st->cnt, CAP);
+    uint64_t k[NPL];
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) {
+        const int i = r * 32 + lane;
+        k[r] = (i < cnt) ? slots[i] : 0ull;
+    }
+    warp_bitonic_sort_desc<NPL>(k, lane);
+#pragma unroll
+    for (int r = 0; r < NPL / 4; ++r) slots[r * 32 + lane] = k[r];
+    // threshold = key at sorted position kth (kth < KP)
+    uint64_t t = 0ull;
+#pragma unroll
+    for (int r = 0; r < NPL / 4; ++r) {
+        const uint64_t cand = __shfl_sync(0xffffffffu, k[r], kth & 31);
+        if (r == (kth >> 5)) t = cand;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        st->cnt = min(cnt, KP);
+        const bool full = cnt > kth;
+        st->thr_key = full ? t : 0ull;
+        st->thr_score = full ? key_score(t) : -INFINITY;
+    }
+    __syncwarp();
+}
+
+// Binary search of `item` in the ascending list items[lo, hi).
+__device__ __forceinline__ bool sorted_contains(const int32_t* __restrict__ items, int64_t lo, int64_t hi, int32_t item)
+{
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        const int32_t v = items[mid];
+        if (v == item) return true;
+        if (v < item)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return false;
+}
+
+}  // namespace gmr

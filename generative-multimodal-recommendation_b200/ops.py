@@ -1,0 +1,276 @@
+"""Tensor-level operators over libgmr.so.
+
+PyTorch is used here for device memory, streams and autograd bookkeeping only; every
+computation below is a call into the hand-written sm_100a kernels through the C ABI
+(``include/gmr.h``).  Nothing in this module has a CPU or eager-PyTorch fallback.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+# Kernel launches issued through this module since import (bench.py reports the delta of a timed
+# region as ``gpu_launches``).
+LAUNCHES = 0
+
+_workspaces = {}
+
+
+def _ws(device, nbytes, tag="default"):
+    """Grow-only per-device scratch buffer (keeps allocations out of the timed/captured path)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _rows(t, name):
+    """(pointer, leading dimension) of a 2-D fp32 CUDA tensor whose rows are contiguous."""
+    if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2):
+        raise TypeError("%s must be a 2-D float32 CUDA tensor, got %s %s on %s" % (name, t.dtype, tuple(t.shape), t.device))
+    if t.shape[1] > 1 and t.stride(1) != 1:
+        raise ValueError("%s must have unit stride along its last dimension" % name)
+    ld = t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+    return _ptr(t), int(ld)
+
+
+class GraphCSR:
+    """A sparse fp32 matrix in CSR form on one GPU plus its SpMM plan (the row schedule).
+
+    The reference keeps its graphs as uncoalesced COO tensors built with the legacy
+    ``torch.sparse.FloatTensor`` ctor (GenMMRec/src/models/diffmm.py:105-107) and pays a coalesce +
+    CSR conversion inside every ``torch.sparse.mm`` on CUDA; here the conversion happens once.
+    Duplicate entries are kept (they add up, exactly like the uncoalesced COO product).
+    """
+
+    def __init__(self, rowptr, col, val, shape, chunk_nnz=0):
+        assert rowptr.dtype == torch.int32 and col.dtype == torch.int32 and val.dtype == torch.float32
+        assert rowptr.is_cuda and col.is_cuda and val.is_cuda
+        self.rowptr, self.col, self.val = rowptr.contiguous(), col.contiguous(), val.contiguous()
+        self.shape = (int(shape[0]), int(shape[1]))
+        self.device = rowptr.device
+        self.chunk_nnz = chunk_nnz
+        self._plan = None
+        self._t = None
+        self._coo = None
+
+    # ---- construction -------------------------------------------------------------------------
+    @classmethod
+    def from_coo(cls, indices, values, shape, device, chunk_nnz=0):
+        """indices [2, nnz] (numpy or tensor, any int type), values [nnz]; entries keep their
+        relative order inside each row (stable sort by row)."""
+        idx = torch.as_tensor(np.asarray(indices) if not torch.is_tensor(indices) else indices)
+        val = torch.as_tensor(np.asarray(values) if not torch.is_tensor(values) else values)
+        idx = idx.to(device=device, dtype=torch.int64)
+        val = val.to(device=device, dtype=torch.float32)
+        n_rows = int(shape[0])
+        if idx.shape[1] >= 2 ** 31 or max(shape) >= 2 ** 31:
+            raise ValueError("graph exceeds the int32 index range of libgmr")
+        if idx.shape[1] > 0 and bool((idx[0, 1:] < idx[0, :-1]).any()):
+            order = torch.sort(idx[0], stable=True).indices
+            idx, val = idx[:, order], val[order]
+        counts = torch.bincount(idx[0], minlength=n_rows) if idx.shape[1] > 0 else \
+            torch.zeros(n_rows, dtype=torch.int64, device=device)
+        rowptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=device)
+        rowptr[1:] = torch.cumsum(counts, 0)
+        g = cls(rowptr.to(torch.int32), idx[1].to(torch.int32), val, shape, chunk_nnz)
+        return g
+
+    @classmethod
+    def from_torch_sparse(cls, t, device=None, chunk_nnz=0):
+        """From a (possibly uncoalesced) torch sparse COO tensor, e.g. the reference's own graphs."""
+        device = device if device is not None else t.device
+        return cls.from_coo(t._indices(), t._values(), tuple(t.shape), device, chunk_nnz)
+
+    @property
+    def nnz(self):
+        return int(self.col.numel())
+
+    def to_torch_coo(self):
+        """Uncoalesced COO view (row-major order) for interop / checks."""
+        counts = (self.rowptr[1:] - self.rowptr[:-1]).to(torch.int64)
+        rows = torch.repeat_interleave(torch.arange(self.shape[0], device=self.device), counts)
+        return torch.sparse_coo_tensor(torch.stack([rows, self.col.to(torch.int64)]), self.val, self.shape)
+
+    def t(self):
+        """Transposed graph (cached); needed by the SpMM backward, and equal to `self` only for
+        symmetric matrices (norm_adj is; the edge-dropped modality graphs and the kNN graphs are not)."""
+        if self._t is None:
+            counts = (self.rowptr[1:] - self.rowptr[:-1]).to(torch.int64)
+            rows = torch.repeat_interleave(torch.arange(self.shape[0], device=self.device), counts)
+            self._t = GraphCSR.from_coo(torch.stack([self.col.to(torch.int64), rows]), self.val,
+                                        (self.shape[1], self.shape[0]), self.device, self.chunk_nnz)
+            self._t._t = self
+        return self._t
+
+    def row_block(self, r0, r1):
+        """CSR of rows [r0, r1) (all columns): the shard a rank owns under row sharding."""
+        rp = self.rowptr[r0:r1 + 1].to(torch.int64)
+        lo, hi = int(rp[0]), int(rp[-1])
+        return GraphCSR((rp - lo).to(torch.int32), self.col[lo:hi].clone(), self.val[lo:hi].clone(),
+                        (r1 - r0, self.shape[1]), self.chunk_nnz)
+
+    # ---- plan -----------------------------------------------------------------------------------
+    @property
+    def plan(self):
+        if self._plan is None:
+            lib = _lib.load()
+            h = C.c_void_p()
+            with torch.cuda.device(self.device):
+                _lib.check(lib.gmr_spmm_plan_create(C.byref(h), _ptr(self.rowptr), self.shape[0], self.shape[1],
+                                                    self.chunk_nnz, _stream()), "gmr_spmm_plan_create")
+            self._plan = h
+        return self._plan
+
+    def plan_stats(self):
+        lib = _lib.load()
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(lib.gmr_spmm_plan_stats(self.plan, C.byref(a), C.byref(b), C.byref(c)), "gmr_spmm_plan_stats")
+        return {"chunks": a.value, "split_rows": b.value, "nnz": c.value}
+
+    def algorithmic_bytes(self, d):
+        """CSR read once + X read once + Y written once."""
+        return self.nnz * 8 + (self.shape[0] + 1) * 4 + self.shape[1] * d * 4 + self.shape[0] * d * 4
+
+    def __del__(self):
+        try:
+            if self._plan is not None and _lib._lib is not None:
+                _lib._lib.gmr_spmm_plan_destroy(self._plan)
+        except Exception:
+            pass
+
+
+def spmm_raw(a, x, out=None, alpha=1.0, beta=0.0):
+    """Y = alpha * A @ X + beta * Y through K1 (no autograd).  `out` may be a column slice of a
+    wider row-major buffer; so may `x`."""
+    global LAUNCHES
+    lib = _lib.load()
+    if x.shape[0] != a.shape[1]:
+        raise ValueError("spmm: A is %s but X has %d rows" % (a.shape, x.shape[0]))
+    d = int(x.shape[1])
+    if out is None:
+        if beta != 0.0:
+            raise ValueError("spmm: beta != 0 needs an `out` to accumulate into")
+        out = torch.empty((a.shape[0], d), dtype=torch.float32, device=x.device)
+    xp, ldx = _rows(x, "X")
+    yp, ldy = _rows(out, "Y")
+    if out.shape != (a.shape[0], d):
+        raise ValueError("spmm: out has shape %s, expected %s" % (tuple(out.shape), (a.shape[0], d)))
+    plan = a.plan
+    need = lib.gmr_spmm_workspace_bytes(plan, d)
+    ws = _ws(x.device, need, "spmm") if need > 0 else None
+    with torch.cuda.device(x.device):
+        _lib.check(lib.gmr_spmm_csr_f32(plan, _ptr(a.rowptr), _ptr(a.col), _ptr(a.val), xp, ldx, yp, ldy, d,
+                                        float(alpha), float(beta), _ptr(ws), need, _stream()), "gmr_spmm_csr_f32")
+    LAUNCHES += 1 + (1 if need > 0 else 0)
+    return out
+
+
+class _SpMM(torch.autograd.Function):
+    """torch.sparse.mm(A, X) with constant A: backward is K1 on the transposed graph
+    (operator contract of SURVEY.md section 8b)."""
+
+    @staticmethod
+    def forward(ctx, x, a):
+        ctx.graph = a
+        return spmm_raw(a, x.contiguous() if x.stride(-1) != 1 else x)
+
+    @staticmethod
+    def backward(ctx, grad):
+        g = grad if grad.stride(-1) == 1 else grad.contiguous()
+        return spmm_raw(ctx.graph.t(), g), None
+
+
+def spmm(a, x):
+    """Drop-in for ``torch.sparse.mm(A, X)`` / ``torch.spmm(A, X)`` with A a GraphCSR."""
+    if x.requires_grad and torch.is_grad_enabled():
+        return _SpMM.apply(x, a)
+    return spmm_raw(a, x)
+
+
+def rows_axpby_norm(x, y=None, z=None, a=1.0, b=0.0, c=0.0, eps=1e-12, out=None):
+    """out = a*x + b*y + c * z / max(||z||_2, eps) row-wise (glue of diffmm.py:138-167)."""
+    global LAUNCHES
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty_like(x)
+    xp, ldx = _rows(x, "x")
+    yp, ldy = _rows(y, "y") if y is not None else (C.c_void_p(0), 0)
+    zp, ldz = _rows(z, "z") if z is not None else (C.c_void_p(0), 0)
+    op, ldo = _rows(out, "out")
+    with torch.cuda.device(x.device):
+        _lib.check(lib.gmr_rows_axpby_norm_f32(xp, ldx, yp, ldy, zp, ldz, op, ldo, x.shape[0], x.shape[1], float(a),
+                                               float(b), float(c), float(eps), _stream()), "gmr_rows_axpby_norm_f32")
+    LAUNCHES += 1
+    return out
+
+
+def score_mask_topk(eu, ei, k, users=None, bias=None, mask_rowptr=None, mask_items=None, precision="fp32",
+                    return_scores=True):
+    """Fused full-sort scoring + train-history mask + top-K (K2).
+
+    eu [*, D], ei [I, D] fp32; users int64 [B] row ids into eu (None: all rows in order);
+    mask_rowptr int64 [B+1] / mask_items int32 ascending within each row.  Returns
+    (ids int32 [B, k], scores fp32 [B, k] or None) ordered by (score desc, item id asc).
+    """
+    global LAUNCHES
+    lib = _lib.load()
+    mode = {"fp32": _lib.GMR_SCORE_FP32, "tc": _lib.GMR_SCORE_TC}[precision]
+    eup, lde_u = _rows(eu, "eu")
+    eip, lde_i = _rows(ei, "ei")
+    if eu.shape[1] != ei.shape[1]:
+        raise ValueError("score_mask_topk: embedding widths differ (%d vs %d)" % (eu.shape[1], ei.shape[1]))
+    b = int(users.numel()) if users is not None else int(eu.shape[0])
+    i, d = int(ei.shape[0]), int(ei.shape[1])
+    if users is not None and not (users.dtype == torch.int64 and users.is_cuda and users.is_contiguous()):
+        raise TypeError("users must be a contiguous int64 CUDA tensor")
+    if bias is not None and not (bias.dtype == torch.float32 and bias.is_cuda and bias.is_contiguous() and bias.numel() == i):
+        raise TypeError("bias must be a contiguous float32 CUDA tensor of length n_items")
+    if mask_rowptr is not None:
+        if not (mask_rowptr.dtype == torch.int64 and mask_rowptr.numel() == b + 1 and mask_rowptr.is_contiguous()):
+            raise TypeError("mask_rowptr must be contiguous int64 of length B + 1")
+        if not (mask_items.dtype == torch.int32 and mask_items.is_contiguous()):
+            raise TypeError("mask_items must be contiguous int32")
+    ids = torch.empty((b, k), dtype=torch.int32, device=eu.device)
+    scores = torch.empty((b, k), dtype=torch.float32, device=eu.device) if return_scores else None
+    need = lib.gmr_score_topk_workspace_bytes(b, i, d, k, mode)
+    ws = _ws(eu.device, need, "score")
+    with torch.cuda.device(eu.device):
+        _lib.check(lib.gmr_score_mask_topk_f32(eup, lde_u, _ptr(users), b, eip, lde_i, _ptr(bias), i, d,
+                                               _ptr(mask_rowptr), _ptr(mask_items), k, mode, _ptr(ids), _ptr(scores),
+                                               _ptr(ws), need, _stream()), "gmr_score_mask_topk_f32")
+    LAUNCHES += 1
+    return ids, scores
+
+
+def hits_metrics(topk, gt_rowptr, gt_items, return_hit=False):
+    """Hit matrix + per-position SUMS over users of recall / ndcg / precision / map (K4).
+    topk int32 [U, K]; ground truth CSR (int64 rowptr, int32 items ascending within a row)."""
+    global LAUNCHES
+    lib = _lib.load()
+    if not (topk.dtype == torch.int32 and topk.is_cuda and topk.is_contiguous() and topk.dim() == 2):
+        raise TypeError("topk must be a contiguous int32 CUDA tensor [U, K]")
+    u, k = int(topk.shape[0]), int(topk.shape[1])
+    if not (gt_rowptr.dtype == torch.int64 and gt_rowptr.numel() == u + 1 and gt_items.dtype == torch.int32):
+        raise TypeError("ground truth must be (int64 rowptr [U+1], int32 items)")
+    hit = torch.empty((u, k), dtype=torch.uint8, device=topk.device) if return_hit else None
+    sums = torch.empty((4, k), dtype=torch.float64, device=topk.device)
+    need = lib.gmr_hits_metrics_workspace_bytes(u, k)
+    ws = _ws(topk.device, need, "metrics")
+    with torch.cuda.device(topk.device):
+        _lib.check(lib.gmr_hits_metrics(_ptr(topk), _ptr(gt_rowptr.contiguous()), _ptr(gt_items.contiguous()), u, k,
+                                        _ptr(hit), _ptr(sums), _ptr(ws), need, _stream()), "gmr_hits_metrics")
+    LAUNCHES += 2
+    return sums, hit

@@ -1,0 +1,159 @@
+/*
+ * gmr.h -- C ABI of libgmr.so, the sm_100a implementation of GenMMRec's hot path.
+ *
+ * The reference (orangeai-research/Generative-Multimodal-Recommendation) is pure Python and has no
+ * FFI of its own; on this path it calls four PyTorch library operators.  Each entry point below
+ * replaces one of those call sites (cited per function, paths relative to the reference root) and
+ * is what a ctypes stub added to the reference would bind (INTEGRATION.md shows that stub).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types cross the boundary.
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in _host.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Calls only enqueue
+ *     work on that stream; they never synchronise unless documented.
+ *   - return value: 0 on success, a negative GMR_ERR_* code otherwise; gmr_last_error() returns a
+ *     thread-local description of the last failure.  No C++ exception crosses the ABI.
+ *   - the caller owns every buffer, including workspaces (sizes are queried with the matching
+ *     *_workspace_bytes call); plan handles own only their private schedule arrays.
+ *   - indices are int32 (N, nnz < 2^31), values/embeddings fp32, row-major with explicit leading
+ *     dimensions in ELEMENTS.
+ */
+#ifndef GMR_H_
+#define GMR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GMR_OK 0
+#define GMR_ERR_INVALID (-1)     /* bad argument (null pointer, negative size, unsupported K ...) */
+#define GMR_ERR_CUDA (-2)        /* a CUDA runtime call failed; see gmr_last_error() */
+#define GMR_ERR_UNSUPPORTED (-3) /* shape/mode not implemented by this build */
+#define GMR_ERR_WORKSPACE (-4)   /* workspace too small */
+
+#define GMR_ABI_VERSION 1
+
+/* Largest K the fused top-K kernels accept. */
+#define GMR_MAX_TOPK 256
+
+const char* gmr_last_error(void);
+int gmr_abi_version(void);
+/* SM count, compute capability and L2 size of the current device. */
+int gmr_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* l2_bytes);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  CSR SpMM:  Y = alpha * A * X + beta * Y
+ * replaces  torch.sparse.mm / torch.spmm(A_coo, X)
+ *   GenMMRec/src/models/diffmm.py:136,139,142,146,149,152,284-285   (forward_MM, GCNLayer)
+ *   GenMMRec/src/models/gume.py:216,226,241,247                      (conv_ui, conv_ii, R)
+ *   GenMMRec/src/models/genrecv1.py:259,279,284,289,294              (user_item_GCN, item_item_GCN)
+ *   GenMMRec/src/models/lightgcn.py:122   GenMMRec/src/models/ld4mrec.py:206
+ *
+ * A is CSR (rowptr int32[n_rows+1], col int32[nnz], val fp32[nnz]); duplicates allowed (they add,
+ * as in an uncoalesced COO).  X is [n_cols, D] with leading dimension ldx, Y is [n_rows, D] with
+ * ldy.  beta == 0 means Y is write-only (it may hold NaNs).  Every D >= 1 is accepted; D % 4 == 0
+ * with 16-byte aligned X/Y rows takes the 128-bit gather path.
+ *
+ * A plan holds the row schedule of one sparsity pattern (rows cut into chunks of at most
+ * `chunk_nnz` nonzeros so that one warp never owns a long row; chunk partial sums of split rows go
+ * through the workspace and are reduced in a fixed order -> results are run-to-run deterministic).
+ * Plan creation reads rowptr back to the host and synchronises `stream`; do it once per graph.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct gmr_spmm_plan gmr_spmm_plan_t;
+
+int gmr_spmm_plan_create(gmr_spmm_plan_t** plan, const int32_t* rowptr, int64_t n_rows, int64_t n_cols,
+                         int32_t chunk_nnz /* 0 = default */, void* stream);
+int gmr_spmm_plan_destroy(gmr_spmm_plan_t* plan);
+/* number of virtual rows (chunks) and of split (multi-chunk) rows, for diagnostics */
+int gmr_spmm_plan_stats(const gmr_spmm_plan_t* plan, int64_t* n_chunks, int64_t* n_split_rows, int64_t* nnz);
+int64_t gmr_spmm_workspace_bytes(const gmr_spmm_plan_t* plan, int32_t D);
+
+int gmr_spmm_csr_f32(const gmr_spmm_plan_t* plan, const int32_t* rowptr, const int32_t* col, const float* val,
+                     const float* X, int64_t ldx, float* Y, int64_t ldy, int32_t D, float alpha, float beta,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Same product, with the result rows additionally PUSHED to peer buffers (fused all-gather of the
+ * row-sharded layer output over NVLink peer memory): rank-local rows [0, n_rows) of this shard are
+ * written to y_peers[p] + (row_offset + r) * ldy for every p in [0, n_peers).  y_peers is a
+ * DEVICE array of n_peers device pointers (peer-mapped); the caller synchronises the ranks. */
+int gmr_spmm_csr_f32_push(const gmr_spmm_plan_t* plan, const int32_t* rowptr, const int32_t* col, const float* val,
+                          const float* X, int64_t ldx, float* const* y_peers, int32_t n_peers, int64_t row_offset,
+                          int64_t ldy, int32_t D, float alpha, void* workspace, int64_t workspace_bytes,
+                          void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2  fused score + train-history mask + top-K (the [B, I] score matrix is never written)
+ * replaces  torch.matmul(u_e[user], i_e.T)  ->  scores[mask] = -1e10  ->  torch.topk(scores, K)
+ *   GenMMRec/src/models/diffmm.py:276-278, gume.py:420-428, genrecv1.py:417-427, vbpr.py:100-106,
+ *   lightgcn.py:156-164, ld4mrec.py:36,54 (output_proj: bias != NULL)
+ *   GenMMRec/src/common/trainer.py:381-386
+ *
+ * score(b, i) = bias[i] + sum_d Eu[users[b], d] * Ei[i, d]  evaluated as the fp32 chain
+ * s = bias[i]; for d = 0..D-1: s = fmaf(u[d], e[d], s)   (bias NULL -> s starts at +0.0f).
+ * Masked pairs score exactly -1e10f.  Results are ordered by (score descending, item id
+ * ascending) -- a total order, so the output is unique.
+ *
+ * users:        int64[B] row ids into Eu, or NULL for rows 0..B-1
+ * mask_rowptr:  int64[B+1] (or NULL: no mask), mask_items int32, ascending within each row
+ * out_ids:      int32[B, K]   out_scores: fp32[B, K] or NULL
+ * precision:    GMR_SCORE_FP32    CUDA-core fp32 FMA scoring
+ *               GMR_SCORE_TC      tcgen05 split-bf16 scoring + exact fp32 re-scoring of the K'
+ *                                 best candidates; rows whose candidate margin cannot certify
+ *                                 exactness are redone on the fp32 path, so both modes return the
+ *                                 same ids.  Requires D % 16 == 0, D <= 256.
+ * 1 <= K <= GMR_MAX_TOPK; if fewer than K items exist the tail is (-1, -inf).
+ * ------------------------------------------------------------------------------------------- */
+#define GMR_SCORE_FP32 0
+#define GMR_SCORE_TC 1
+
+int64_t gmr_score_topk_workspace_bytes(int32_t B, int32_t I, int32_t D, int32_t K, int32_t precision);
+
+int gmr_score_mask_topk_f32(const float* Eu, int64_t lde_u, const int64_t* users, int32_t B, const float* Ei,
+                            int64_t lde_i, const float* bias, int32_t I, int32_t D, const int64_t* mask_rowptr,
+                            const int32_t* mask_items, int32_t K, int32_t precision, int32_t* out_ids,
+                            float* out_scores, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K4  hit matrix + Recall / NDCG / Precision / MAP prefix sums
+ * replaces  the Python membership loop and the numpy metric kernels
+ *   GenMMRec/src/utils/topk_evaluator.py:107-120,299-313   GenMMRec/src/utils/metrics.py:12-105
+ *
+ * topk int32[U, K]; ground truth as CSR over eval users (gt_rowptr int64[U+1], gt_items int32
+ * ascending within a row, length >= 1 per user).  Writes hit uint8[U, K] (or NULL) and
+ * sums double[4, K] = per-position SUMS over users of recall, ndcg, precision, map (the caller
+ * divides by the user count, after an all-reduce when users are sharded).  Deterministic.
+ * ------------------------------------------------------------------------------------------- */
+int64_t gmr_hits_metrics_workspace_bytes(int32_t U, int32_t K);
+int gmr_hits_metrics(const int32_t* topk, const int64_t* gt_rowptr, const int32_t* gt_items, int32_t U, int32_t K,
+                     uint8_t* hit, double* sums, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Row-wise glue of the propagation step (a7 in SURVEY.md section 8): fused so that a layer costs
+ * one pass over [N, D] instead of ~10 (F.normalize / axpy / layer sums of
+ * GenMMRec/src/models/diffmm.py:138-167).
+ *   out[r, :] = a * x[r, :] + b * y[r, :] + c * z[r, :] / max(||z[r, :]||_2, eps)
+ * y and/or z may be NULL (their terms vanish).  out may alias x or y.
+ * ------------------------------------------------------------------------------------------- */
+int gmr_rows_axpby_norm_f32(const float* x, int64_t ldx, const float* y, int64_t ldy, const float* z, int64_t ldz,
+                            float* out, int64_t ldo, int64_t n_rows, int32_t D, float a, float b, float c,
+                            float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Peer-memory plumbing for the fused SpMM + all-gather (CUDA IPC, one process per GPU).
+ * gmr_peer_alloc allocates `bytes` of device memory suitable for export; gmr_peer_export fills a
+ * 64-byte handle; another process maps it with gmr_peer_open.  The Python host exchanges the
+ * handles through torch.distributed.
+ * ------------------------------------------------------------------------------------------- */
+#define GMR_PEER_HANDLE_BYTES 64
+int gmr_peer_alloc(void** ptr, int64_t bytes);
+int gmr_peer_free(void* ptr);
+int gmr_peer_export(void* ptr, uint8_t* handle_host /* [GMR_PEER_HANDLE_BYTES] */);
+int gmr_peer_open(const uint8_t* handle_host, void** ptr);
+int gmr_peer_close(void* ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GMR_H_ */

@@ -1,0 +1,200 @@
+"""Parity of the CUDA kernels (through the C ABI) against the C oracle on seeded inputs, including
+the edge cases the domain has: empty rows, duplicate entries, rows longer than the chunk (split
+rows), ragged widths, masks that leave fewer than K items, ties, K at the limits."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_api
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from genmmrec_b200 import ops as _ops
+    return _ops
+
+
+def random_csr(rng, n_rows, n_cols, avg, long_rows=(), empty_rows=()):
+    deg = rng.poisson(avg, size=n_rows).astype(np.int64)
+    for r, n in long_rows:
+        deg[r] = n
+    for r in empty_rows:
+        deg[r] = 0
+    rowptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+    col = rng.integers(0, n_cols, size=int(rowptr[-1])).astype(np.int32)  # duplicates allowed
+    val = rng.standard_normal(col.size).astype(np.float32)
+    return rowptr, col, val
+
+
+def to_graph(ops, rowptr, col, val, shape, chunk=0):
+    dev = torch.device("cuda:0")
+    return ops.GraphCSR(torch.from_numpy(rowptr).to(dev), torch.from_numpy(col).to(dev), torch.from_numpy(val).to(dev),
+                        shape, chunk_nnz=chunk)
+
+
+def rel(a, b):
+    return np.abs(a.astype(np.float64) - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+@pytest.mark.parametrize("d", [64, 128, 192, 32, 20, 7, 1, 516])
+def test_spmm_matches_oracle(ops, d):
+    rng = np.random.default_rng(d)
+    n_rows, n_cols = 3000, 2500
+    rowptr, col, val = random_csr(rng, n_rows, n_cols, 20, long_rows=[(7, 5000), (1500, 700), (2999, 257)],
+                                  empty_rows=[0, 11, 2998])
+    x = rng.standard_normal((n_cols, d)).astype(np.float32)
+    g = to_graph(ops, rowptr, col, val, (n_rows, n_cols))
+    assert g.plan_stats()["split_rows"] == 3
+    y = ops.spmm_raw(g, torch.from_numpy(x).cuda()).cpu().numpy()
+    y64 = c_api.spmm_csr_f64(rowptr, col, val, x)
+    y32 = c_api.spmm_csr(rowptr, col, val, x)
+    # tolerance of the north star: 1e-5 relative (fp32), per matrix
+    assert rel(y, y64) < 1e-5
+    assert rel(y32, y64) < 1e-5
+    assert np.all(y[0] == 0) and np.all(y[11] == 0)
+    # determinism: split rows are reduced in a fixed order
+    y2 = ops.spmm_raw(g, torch.from_numpy(x).cuda()).cpu().numpy()
+    assert np.array_equal(y, y2)
+
+
+def test_spmm_alpha_beta_and_strided_views(ops):
+    rng = np.random.default_rng(3)
+    n_rows, n_cols, d = 1000, 800, 64
+    rowptr, col, val = random_csr(rng, n_rows, n_cols, 9, long_rows=[(5, 900)])
+    g = to_graph(ops, rowptr, col, val, (n_rows, n_cols))
+    xw = torch.from_numpy(rng.standard_normal((n_cols, 192)).astype(np.float32)).cuda()
+    yw = torch.from_numpy(rng.standard_normal((n_rows, 192)).astype(np.float32)).cuda()
+    y0 = yw.clone()
+    x = xw[:, 64:128]
+    ops.spmm_raw(g, x, out=yw[:, 128:192], alpha=0.5, beta=2.0)
+    ref = 0.5 * c_api.spmm_csr_f64(rowptr, col, val, x.cpu().numpy()) + 2.0 * y0[:, 128:192].cpu().numpy()
+    assert rel(yw[:, 128:192].cpu().numpy(), ref) < 1e-5
+    assert torch.equal(yw[:, :128], y0[:, :128])  # neighbours of the slice untouched
+
+
+def test_spmm_chunk_sizes_agree(ops):
+    rng = np.random.default_rng(4)
+    rowptr, col, val = random_csr(rng, 500, 400, 40, long_rows=[(3, 3000)])
+    x = torch.from_numpy(rng.standard_normal((400, 64)).astype(np.float32)).cuda()
+    ref = c_api.spmm_csr_f64(rowptr, col, val, x.cpu().numpy())
+    for chunk in (32, 64, 256, 4096):
+        g = to_graph(ops, rowptr, col, val, (500, 400), chunk=chunk)
+        assert rel(ops.spmm_raw(g, x).cpu().numpy(), ref) < 1e-5
+
+
+def test_spmm_backward_is_transpose(ops):
+    rng = np.random.default_rng(5)
+    rowptr, col, val = random_csr(rng, 300, 200, 6)
+    g = to_graph(ops, rowptr, col, val, (300, 200))
+    x = torch.from_numpy(rng.standard_normal((200, 64)).astype(np.float32)).cuda().requires_grad_(True)
+    w = torch.from_numpy(rng.standard_normal((300, 64)).astype(np.float32)).cuda()
+    (ops.spmm(g, x) * w).sum().backward()
+    dense = g.to_torch_coo().to_dense().double()
+    assert rel(x.grad.cpu().numpy(), (dense.T @ w.double()).cpu().numpy()) < 1e-5
+
+
+def make_mask(rng, b, n_items, avg):
+    lens = rng.poisson(avg, size=b)
+    rowptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    items = np.concatenate([np.sort(rng.choice(n_items, size=n, replace=False)) for n in lens] + [np.zeros(0, np.int64)])
+    return rowptr, items.astype(np.int32)
+
+
+@pytest.mark.parametrize("n_items,d,k,with_bias", [(7050, 64, 50, False), (1000, 128, 20, False), (333, 256, 64, True),
+                                                   (130, 64, 128, False), (5000, 60, 5, True), (900, 64, 200, False)])
+def test_score_mask_topk_bit_exact(ops, n_items, d, k, with_bias):
+    rng = np.random.default_rng(n_items + d)
+    n_users, b = 700, 389
+    eu = rng.standard_normal((n_users, d)).astype(np.float32)
+    ei = rng.standard_normal((n_items, d)).astype(np.float32)
+    ei[17] = ei[3]  # exact score ties between two items -> id order decides
+    users = rng.choice(n_users, size=b, replace=False).astype(np.int64)
+    bias = rng.standard_normal(n_items).astype(np.float32) if with_bias else None
+    mrp, mit = make_mask(rng, b, n_items, 30)
+    ids_ref, sc_ref = c_api.score_mask_topk(eu, users, ei, bias, mrp, mit, k)
+    ids, sc = ops.score_mask_topk(torch.from_numpy(eu).cuda(), torch.from_numpy(ei).cuda(), k,
+                                  users=torch.from_numpy(users).cuda(),
+                                  bias=None if bias is None else torch.from_numpy(bias).cuda(),
+                                  mask_rowptr=torch.from_numpy(mrp).cuda(), mask_items=torch.from_numpy(mit).cuda())
+    assert np.array_equal(ids.cpu().numpy(), ids_ref)
+    assert np.array_equal(sc.cpu().numpy(), sc_ref)
+
+
+def test_score_topk_fewer_unmasked_than_k(ops):
+    """trainer.py:384 writes the finite -1e10: masked items surface once the unmasked run out."""
+    rng = np.random.default_rng(9)
+    n_items, d, k = 40, 64, 32
+    eu = rng.standard_normal((5, d)).astype(np.float32)
+    ei = rng.standard_normal((n_items, d)).astype(np.float32)
+    lens = np.array([0, 10, 20, 39, 40])
+    mrp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    mit = np.concatenate([np.sort(rng.choice(n_items, size=n, replace=False)) for n in lens]).astype(np.int32)
+    ids_ref, sc_ref = c_api.score_mask_topk(eu, None, ei, None, mrp, mit, k)
+    ids, sc = ops.score_mask_topk(torch.from_numpy(eu).cuda(), torch.from_numpy(ei).cuda(), k,
+                                  mask_rowptr=torch.from_numpy(mrp).cuda(), mask_items=torch.from_numpy(mit).cuda())
+    assert np.array_equal(ids.cpu().numpy(), ids_ref)
+    assert np.array_equal(sc.cpu().numpy(), sc_ref)
+    assert (sc.cpu().numpy()[4] == -1e10).all()
+
+
+def test_score_topk_k_larger_than_items(ops):
+    rng = np.random.default_rng(10)
+    eu = rng.standard_normal((3, 64)).astype(np.float32)
+    ei = rng.standard_normal((10, 64)).astype(np.float32)
+    ids_ref, sc_ref = c_api.score_mask_topk(eu, None, ei, None, None, None, 16)
+    ids, sc = ops.score_mask_topk(torch.from_numpy(eu).cuda(), torch.from_numpy(ei).cuda(), 16)
+    assert np.array_equal(ids.cpu().numpy(), ids_ref)
+    assert (ids.cpu().numpy()[:, 10:] == -1).all() and np.isneginf(sc.cpu().numpy()[:, 10:]).all()
+
+
+def test_score_topk_adversarial_order(ops):
+    """Scores increasing with the item id: every tile beats the running threshold (worst case for
+    the append buffers, exercises the overflow/retry path)."""
+    n_items, d, k = 6000, 64, 50
+    eu = np.zeros((130, d), dtype=np.float32)
+    eu[:, 0] = 1.0
+    ei = np.zeros((n_items, d), dtype=np.float32)
+    ei[:, 0] = np.arange(n_items, dtype=np.float32)
+    ids, sc = ops.score_mask_topk(torch.from_numpy(eu).cuda(), torch.from_numpy(ei).cuda(), k)
+    want = np.arange(n_items - 1, n_items - 1 - k, -1, dtype=np.int32)
+    assert (ids.cpu().numpy() == want[None, :]).all()
+
+
+@pytest.mark.parametrize("k", [50, 20, 1, 64, 200])
+def test_hits_metrics_match_oracle(ops, k):
+    rng = np.random.default_rng(k)
+    u, n_items = 1000, 400
+    topk = np.stack([rng.choice(n_items, size=k, replace=False) for _ in range(u)]).astype(np.int32)
+    lens = rng.integers(1, 80, size=u)
+    rowptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    items = np.concatenate([np.sort(rng.choice(n_items, size=n, replace=False)) for n in lens]).astype(np.int32)
+    hit_ref = c_api.hits(topk, rowptr, items)
+    m_ref = c_api.metrics(hit_ref, lens)
+    sums, hit = ops.hits_metrics(torch.from_numpy(topk).cuda(), torch.from_numpy(rowptr).cuda(),
+                                 torch.from_numpy(items).cuda(), return_hit=True)
+    assert np.array_equal(hit.cpu().numpy(), hit_ref)  # integer work: bit-exact
+    got = (sums / u).cpu().numpy()
+    for j, m in enumerate(("recall", "ndcg", "precision", "map")):
+        assert np.abs(got[j] - m_ref[m]).max() < 1e-12, m
+
+
+def test_rows_axpby_norm(ops):
+    rng = np.random.default_rng(12)
+    x, y, z = (torch.from_numpy(rng.standard_normal((500, 64)).astype(np.float32)).cuda() for _ in range(3))
+    out = ops.rows_axpby_norm(x, y, z, a=1.0, b=0.3, c=0.5)
+    ref = x + 0.3 * y + 0.5 * torch.nn.functional.normalize(z)
+    assert rel(out.cpu().numpy(), ref.double().cpu().numpy()) < 1e-6
+
+
+def test_errors_are_loud(ops):
+    rng = np.random.default_rng(13)
+    rowptr, col, val = random_csr(rng, 10, 10, 3)
+    g = to_graph(ops, rowptr, col, val, (10, 10))
+    with pytest.raises(ValueError):
+        ops.spmm_raw(g, torch.zeros((11, 64), device="cuda"))
+    with pytest.raises(RuntimeError):
+        ops.score_mask_topk(torch.zeros((4, 64), device="cuda"), torch.zeros((9, 64), device="cuda"), 1000)
