@@ -34,6 +34,9 @@ int score_topk_simt_launch(const float* Eu, int64_t lde_u, const int64_t* users,
                            int32_t n_rows, const float* Ei, int64_t lde_i, const float* bias, int32_t I, int32_t D,
                            const int64_t* mask_rowptr, const int32_t* mask_items, int32_t K, int32_t* out_ids,
                            float* out_scores, void* workspace, cudaStream_t st, int grid_override);
+int scores_dense_launch(const float* Eu, int64_t lde_u, const int64_t* users, int32_t B, const float* Ei,
+                        int64_t lde_i, const float* bias, int32_t I, int32_t D, float* out, int64_t ldo,
+                        cudaStream_t st);
 // score_topk_tc.cu
 bool score_tc_supported(int32_t D, int32_t K);
 int64_t score_tc_workspace_bytes(int32_t B, int32_t I, int32_t D, int32_t K);
@@ -111,6 +114,17 @@ extern "C" int gmr_score_mask_topk_f32(const float* Eu, int64_t lde_u, const int
     }
     return gmr::score_topk_simt_launch(Eu, lde_u, users, nullptr, B, Ei, lde_i, bias, I, D, mask_rowptr, mask_items,
                                        K, out_ids, out_scores, workspace, st, 0);
+}
+
+extern "C" int gmr_scores_f32(const float* Eu, int64_t lde_u, const int64_t* users, int32_t B, const float* Ei,
+                              int64_t lde_i, const float* bias, int32_t I, int32_t D, float* out, int64_t ldo,
+                              void* stream)
+{
+    GMR_REQUIRE(B >= 0 && I >= 1 && D >= 1, "gmr_scores_f32: bad shape B=%d I=%d D=%d", B, I, D);
+    if (B == 0) return GMR_OK;
+    GMR_REQUIRE(Eu && Ei && out, "gmr_scores_f32: null operand");
+    GMR_REQUIRE(lde_u >= D && lde_i >= D && ldo >= I, "gmr_scores_f32: leading dimension too small");
+    return gmr::scores_dense_launch(Eu, lde_u, users, B, Ei, lde_i, bias, I, D, out, ldo, (cudaStream_t)stream);
 }
 
 // ---- peer memory (CUDA IPC) ---------------------------------------------------------------------

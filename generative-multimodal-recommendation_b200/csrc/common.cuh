@@ -78,7 +78,7 @@ __device__ __forceinline__ float ld_stream_f32(const float* p, uint64_t pol)
 __device__ __forceinline__ float4 ld_gather_f4(const float4* p, uint64_t pol)
 {
     float4 v;
-    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+    asm("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                  : "l"(p), "l"(pol));
     return v;
@@ -86,7 +86,7 @@ __device__ __forceinline__ float4 ld_gather_f4(const float4* p, uint64_t pol)
 __device__ __forceinline__ float ld_gather_f1(const float* p, uint64_t pol)
 {
     float v;
-    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    asm("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
     return v;
 }
 

@@ -249,6 +249,77 @@ __global__ void __launch_bounds__(kThreads, 2) score_topk_simt_kernel(ScoreArgs 
     }
 }
 
+// ---- dense scores (API parity with full_sort_predict; not on the fused evaluation path) -------
+// out[b, i] = bias[i] + sum_d Eu[users[b], d] * Ei[i, d], same fmaf chain as above.
+__global__ void __launch_bounds__(256)
+    scores_dense_kernel(const float* __restrict__ Eu, int64_t lde_u, const int64_t* __restrict__ users, int32_t B,
+                        const float* __restrict__ Ei, int64_t lde_i, const float* __restrict__ bias, int32_t I,
+                        int32_t D, float* __restrict__ out, int64_t ldo)
+{
+    constexpr int T = 64, DKc = 16;
+    __shared__ float As[DKc][T + 1];
+    __shared__ float Bs[DKc][T + 1];
+    const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+    const int u0 = blockIdx.y * T, i0 = blockIdx.x * T;
+    float acc[4][4];
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+        const int item = i0 + tx + 16 * ii;
+        const float bv = (bias != nullptr && item < I) ? bias[item] : 0.f;
+#pragma unroll
+        for (int ui = 0; ui < 4; ++ui) acc[ui][ii] = bv;
+    }
+    for (int d0 = 0; d0 < D; d0 += DKc) {
+        __syncthreads();
+        for (int idx = t; idx < T * DKc; idx += 256) {
+            const int r = idx / DKc, d = idx % DKc;
+            const int b = u0 + r, item = i0 + r;
+            float av = 0.f, bv = 0.f;
+            if (d0 + d < D) {
+                if (b < B) av = Eu[(users ? users[b] : (int64_t)b) * lde_u + d0 + d];
+                if (item < I) bv = Ei[(int64_t)item * lde_i + d0 + d];
+            }
+            As[d][r] = av;
+            Bs[d][r] = bv;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int d = 0; d < DKc; ++d) {
+            float a[4], b[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                a[q] = As[d][ty + 16 * q];
+                b[q] = Bs[d][tx + 16 * q];
+            }
+#pragma unroll
+            for (int ui = 0; ui < 4; ++ui)
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) acc[ui][ii] = fmaf(a[ui], b[ii], acc[ui][ii]);
+        }
+    }
+#pragma unroll
+    for (int ui = 0; ui < 4; ++ui) {
+        const int b = u0 + ty + 16 * ui;
+        if (b >= B) continue;
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+            const int item = i0 + tx + 16 * ii;
+            if (item < I) out[(int64_t)b * ldo + item] = acc[ui][ii];
+        }
+    }
+}
+
+int scores_dense_launch(const float* Eu, int64_t lde_u, const int64_t* users, int32_t B, const float* Ei,
+                        int64_t lde_i, const float* bias, int32_t I, int32_t D, float* out, int64_t ldo,
+                        cudaStream_t st)
+{
+    if (B == 0) return GMR_OK;
+    dim3 grid((I + 63) / 64, (B + 63) / 64);
+    scores_dense_kernel<<<grid, 256, 0, st>>>(Eu, lde_u, users, B, Ei, lde_i, bias, I, D, out, ldo);
+    GMR_LAUNCH_CHECK();
+    return GMR_OK;
+}
+
 static int simt_grid(int32_t B)
 {
     const int tiles = (B + kBU - 1) / kBU;

@@ -97,8 +97,11 @@ struct PushArgs {
 };
 
 // One warp per virtual row.  Vec = float4 (D % 4 == 0, aligned) or float.  DV = row length in Vec.
-template <typename Vec, int LANES, int ITER, bool IDENT, bool PUSH>
-__global__ void __launch_bounds__(kWarps * 32)
+// OFF32: every gathered address fits a 32-bit offset in Vec units (n_cols * ldx / VEC < 2^32), so the
+// staged entry is the row offset itself and the gather address is one IMAD.WIDE away.
+// EXACT: DV == LANES * ITER, no column predicate.
+template <typename Vec, int LANES, int ITER, bool IDENT, bool PUSH, bool OFF32, bool EXACT>
+__global__ void __launch_bounds__(kWarps * 32, (ITER == 1) ? 4 : 2)
     spmm_vrow_kernel(const int32_t* __restrict__ vptr, const int32_t* __restrict__ vrow,
                      const int32_t* __restrict__ col, const float* __restrict__ val, const float* __restrict__ X,
                      int64_t ldx, float* __restrict__ Y, int64_t ldy, float* __restrict__ partial, int32_t DV,
@@ -108,9 +111,9 @@ __global__ void __launch_bounds__(kWarps * 32)
     constexpr int VEC = sizeof(Vec) / 4;
     constexpr int NPS = 32 / LANES;              // nonzeros consumed per warp step
     constexpr int UNROLL = (ITER >= 2) ? 2 : 4;  // steps whose gathers are issued back to back
-    static_assert(32 % (NPS * UNROLL) == 0, "batch must tile the 32-entry stage");
-
-    __shared__ int2 stage[kWarps][32];
+    constexpr int GROUP = NPS * UNROLL;          // nonzeros per unrolled batch
+    constexpr int STAGE = 256;  // (col, val) pairs staged per pass: a whole chunk at the default size
+    __shared__ int2 stage[kWarps][STAGE];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t v = (int64_t)blockIdx.x * kWarps + warp;
@@ -120,43 +123,74 @@ __global__ void __launch_bounds__(kWarps * 32)
     const int dst = IDENT ? (int)v : vrow[v];
     const int sub = lane % LANES, grp = lane / LANES;
     const int vcol0 = blockIdx.y * (LANES * ITER) + sub;  // this lane's first Vec column
+    const uint32_t ldv = (uint32_t)(ldx / VEC);           // row pitch in Vec units (OFF32 only)
+    const Vec* __restrict__ Xl = reinterpret_cast<const Vec*>(X) + vcol0;
+    bool colok[ITER];
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) colok[it] = EXACT || (vcol0 + it * LANES < DV);
 
     const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
     Vec acc[ITER];
 #pragma unroll
     for (int it = 0; it < ITER; ++it) acc[it] = Ops::zero();
 
-    for (int base = begin; base < end; base += 32) {
-        const int n = min(32, end - base);
-        int c = 0;
-        float w = 0.f;
-        if (lane < n) {
-            c = ld_stream_s32(col + base + lane, pol_stream);
-            w = ld_stream_f32(val + base + lane, pol_stream);
+    auto row_ptr = [&](int c) -> const Vec* {
+        if (OFF32) return Xl + (uint32_t)c;  // c is already col * ldv
+        return reinterpret_cast<const Vec*>(X + (int64_t)c * ldx) + vcol0;
+    };
+    const int2* my_stage = stage[warp];
+    // one batch = GROUP nonzeros: UNROLL gathers per lane
+    auto load_group = [&](int g, int2 (&cw)[UNROLL], Vec (&xv)[UNROLL][ITER]) {
+#pragma unroll
+        for (int q = 0; q < UNROLL; ++q) cw[q] = my_stage[g * GROUP + q * NPS + grp];
+#pragma unroll
+        for (int q = 0; q < UNROLL; ++q) {
+            const Vec* xr = row_ptr(cw[q].x);
+#pragma unroll
+            for (int it = 0; it < ITER; ++it)
+                xv[q][it] = colok[it] ? Ops::gather(xr + it * LANES, pol_keep) : Ops::zero();
+        }
+    };
+    auto fma_group = [&](const int2 (&cw)[UNROLL], const Vec (&xv)[UNROLL][ITER]) {
+#pragma unroll
+        for (int q = 0; q < UNROLL; ++q)
+#pragma unroll
+            for (int it = 0; it < ITER; ++it) Ops::fma(acc[it], __int_as_float(cw[q].y), xv[q][it]);
+    };
+
+    for (int base = begin; base < end; base += STAGE) {
+        const int n = min(STAGE, end - base);
+        __syncwarp();
+        for (int k = lane; k < n; k += 32) {  // coalesced CSR stream -> shared memory
+            int c = ld_stream_s32(col + base + k, pol_stream);
+            const float w = ld_stream_f32(val + base + k, pol_stream);
+            if (OFF32) c = (int)((uint32_t)c * ldv);
+            stage[warp][k] = make_int2(c, __float_as_int(w));
         }
         __syncwarp();
-        stage[warp][lane] = make_int2(c, __float_as_int(w));
-        __syncwarp();
-        for (int j = 0; j < n; j += NPS * UNROLL) {
-            Vec xv[UNROLL][ITER];
-            float wq[UNROLL];
-#pragma unroll
-            for (int q = 0; q < UNROLL; ++q) {
-                const int e = j + q * NPS + grp;
-                const int2 cw = stage[warp][e];
-                const bool ok = e < n;
-                wq[q] = ok ? __int_as_float(cw.y) : 0.f;
-                const Vec* xr = reinterpret_cast<const Vec*>(X + (int64_t)cw.x * ldx);
-#pragma unroll
-                for (int it = 0; it < ITER; ++it) {
-                    const int vc = vcol0 + it * LANES;
-                    xv[q][it] = (ok && vc < DV) ? Ops::gather(xr + vc, pol_keep) : Ops::zero();
-                }
+        // software pipeline over full batches: the gathers of batch g+1 are issued before the FMAs of
+        // batch g, so every warp keeps UNROLL..2*UNROLL independent 128-bit gathers in flight
+        const int ng = n / GROUP;
+        if (ng > 0) {
+            int2 cwA[UNROLL], cwB[UNROLL];
+            Vec xA[UNROLL][ITER], xB[UNROLL][ITER];
+            load_group(0, cwA, xA);
+            int g = 0;
+            while (true) {
+                if (g + 1 < ng) load_group(g + 1, cwB, xB);
+                fma_group(cwA, xA);
+                if (++g >= ng) break;
+                if (g + 1 < ng) load_group(g + 1, cwA, xA);
+                fma_group(cwB, xB);
+                if (++g >= ng) break;
             }
+        }
+        for (int e = ng * GROUP + grp; e < n; e += NPS) {  // ragged tail of the row
+            const int2 cw = my_stage[e];
+            const Vec* xr = row_ptr(cw.x);
 #pragma unroll
-            for (int q = 0; q < UNROLL; ++q)
-#pragma unroll
-                for (int it = 0; it < ITER; ++it) Ops::fma(acc[it], wq[q], xv[q][it]);
+            for (int it = 0; it < ITER; ++it)
+                if (colok[it]) Ops::fma(acc[it], __int_as_float(cw.y), Ops::gather(xr + it * LANES, pol_keep));
         }
     }
 
@@ -169,7 +203,7 @@ __global__ void __launch_bounds__(kWarps * 32)
 #pragma unroll
     for (int it = 0; it < ITER; ++it) {
         const int vc = vcol0 + it * LANES;
-        if (vc >= DV) continue;
+        if (!colok[it]) continue;
         if (!IDENT && dst < 0) {
             // chunk of a split row: raw partial sum, reduced later in slot order
             Vec* p = reinterpret_cast<Vec*>(partial + (int64_t)(-1 - dst) * ((int64_t)DV * VEC)) + vc;
@@ -229,10 +263,10 @@ __global__ void __launch_bounds__(kWarps * 32)
     }
 }
 
-template <typename Vec, int LANES, int ITER, bool PUSH>
-static int launch_vrow(const gmr_spmm_plan* plan, const int32_t* rowptr, const int32_t* col, const float* val,
-                       const float* X, int64_t ldx, float* Y, int64_t ldy, float* partial, int32_t DV, float alpha,
-                       float beta, PushArgs push, cudaStream_t st)
+template <typename Vec, int LANES, int ITER, bool PUSH, bool OFF32, bool EXACT>
+static int launch_vrow2(const gmr_spmm_plan* plan, const int32_t* rowptr, const int32_t* col, const float* val,
+                        const float* X, int64_t ldx, float* Y, int64_t ldy, float* partial, int32_t DV, float alpha,
+                        float beta, PushArgs push, cudaStream_t st)
 {
     const bool ident = plan->d_vptr == nullptr;
     const int64_t nv = plan->n_vrows;
@@ -240,14 +274,30 @@ static int launch_vrow(const gmr_spmm_plan* plan, const int32_t* rowptr, const i
     dim3 grid((unsigned)((nv + kWarps - 1) / kWarps), (unsigned)((DV + LANES * ITER - 1) / (LANES * ITER)));
     dim3 block(kWarps * 32);
     if (ident)
-        spmm_vrow_kernel<Vec, LANES, ITER, true, PUSH><<<grid, block, 0, st>>>(rowptr, nullptr, col, val, X, ldx, Y, ldy,
-                                                                             partial, DV, nv, alpha, beta, push);
+        spmm_vrow_kernel<Vec, LANES, ITER, true, PUSH, OFF32, EXACT><<<grid, block, 0, st>>>(
+            rowptr, nullptr, col, val, X, ldx, Y, ldy, partial, DV, nv, alpha, beta, push);
     else
-        spmm_vrow_kernel<Vec, LANES, ITER, false, PUSH><<<grid, block, 0, st>>>(plan->d_vptr, plan->d_vrow, col, val, X,
-                                                                              ldx, Y, ldy, partial, DV, nv, alpha,
-                                                                              beta, push);
+        spmm_vrow_kernel<Vec, LANES, ITER, false, PUSH, OFF32, EXACT><<<grid, block, 0, st>>>(
+            plan->d_vptr, plan->d_vrow, col, val, X, ldx, Y, ldy, partial, DV, nv, alpha, beta, push);
     GMR_LAUNCH_CHECK();
     return GMR_OK;
+}
+
+template <typename Vec, int LANES, int ITER, bool PUSH>
+static int launch_vrow(const gmr_spmm_plan* plan, const int32_t* rowptr, const int32_t* col, const float* val,
+                       const float* X, int64_t ldx, float* Y, int64_t ldy, float* partial, int32_t DV, float alpha,
+                       float beta, PushArgs push, cudaStream_t st)
+{
+    constexpr int VEC = sizeof(Vec) / 4;
+    // 32-bit row offsets (in Vec units) whenever the whole X operand is addressable that way
+    const bool off32 = (ldx % VEC == 0) && ((plan->n_cols + 1) * (ldx / VEC) < (int64_t)0xffffffffll);
+    const bool exact = (DV == LANES * ITER);
+#define GMR_GO(O, E) \
+    return launch_vrow2<Vec, LANES, ITER, PUSH, O, E>(plan, rowptr, col, val, X, ldx, Y, ldy, partial, DV, alpha, beta, push, st)
+    if (off32 && exact) GMR_GO(true, true);
+    if (off32) GMR_GO(true, false);
+    GMR_GO(false, false);
+#undef GMR_GO
 }
 
 template <typename Vec, bool PUSH>

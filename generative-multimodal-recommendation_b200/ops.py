@@ -15,7 +15,26 @@ from . import _lib
 # region as ``gpu_launches``).
 LAUNCHES = 0
 
+# When set to a list, every operator appends (name, meta, start_event, end_event): CUDA events recorded
+# on the launching stream around the C-ABI call (bench.py derives per-kernel durations from them).
+PROFILE = None
+
 _workspaces = {}
+
+
+def _prof_begin():
+    if PROFILE is None:
+        return None
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record()
+    return ev
+
+
+def _prof_end(name, ev, **meta):
+    if ev is not None:
+        end = torch.cuda.Event(enable_timing=True)
+        end.record()
+        PROFILE.append((name, meta, ev, end))
 
 
 def _ws(device, nbytes, tag="default"):
@@ -172,8 +191,10 @@ def spmm_raw(a, x, out=None, alpha=1.0, beta=0.0):
     need = lib.gmr_spmm_workspace_bytes(plan, d)
     ws = _ws(x.device, need, "spmm") if need > 0 else None
     with torch.cuda.device(x.device):
+        ev = _prof_begin()
         _lib.check(lib.gmr_spmm_csr_f32(plan, _ptr(a.rowptr), _ptr(a.col), _ptr(a.val), xp, ldx, yp, ldy, d,
                                         float(alpha), float(beta), _ptr(ws), need, _stream()), "gmr_spmm_csr_f32")
+        _prof_end("spmm", ev, alg_bytes=a.algorithmic_bytes(d), nnz=a.nnz, d=d, rows=a.shape[0], cols=a.shape[1])
     LAUNCHES += 1 + (1 if need > 0 else 0)
     return out
 
@@ -248,11 +269,30 @@ def score_mask_topk(eu, ei, k, users=None, bias=None, mask_rowptr=None, mask_ite
     need = lib.gmr_score_topk_workspace_bytes(b, i, d, k, mode)
     ws = _ws(eu.device, need, "score")
     with torch.cuda.device(eu.device):
+        ev = _prof_begin()
         _lib.check(lib.gmr_score_mask_topk_f32(eup, lde_u, _ptr(users), b, eip, lde_i, _ptr(bias), i, d,
                                                _ptr(mask_rowptr), _ptr(mask_items), k, mode, _ptr(ids), _ptr(scores),
                                                _ptr(ws), need, _stream()), "gmr_score_mask_topk_f32")
+        _prof_end("score_topk", ev, flops=2.0 * b * i * d, users=b, items=i, d=d, k=k, precision=precision)
     LAUNCHES += 1
     return ids, scores
+
+
+def scores_dense(eu, ei, users=None, bias=None):
+    """fp32 [B, I] score matrix (API parity with ``full_sort_predict``; the fused evaluation never
+    materialises it)."""
+    global LAUNCHES
+    lib = _lib.load()
+    eup, lde_u = _rows(eu, "eu")
+    eip, lde_i = _rows(ei, "ei")
+    b = int(users.numel()) if users is not None else int(eu.shape[0])
+    i, d = int(ei.shape[0]), int(ei.shape[1])
+    out = torch.empty((b, i), dtype=torch.float32, device=eu.device)
+    with torch.cuda.device(eu.device):
+        _lib.check(lib.gmr_scores_f32(eup, lde_u, _ptr(users), b, eip, lde_i, _ptr(bias), i, d, _ptr(out), i,
+                                      _stream()), "gmr_scores_f32")
+    LAUNCHES += 1
+    return out
 
 
 def hits_metrics(topk, gt_rowptr, gt_items, return_hit=False):
@@ -270,7 +310,9 @@ def hits_metrics(topk, gt_rowptr, gt_items, return_hit=False):
     need = lib.gmr_hits_metrics_workspace_bytes(u, k)
     ws = _ws(topk.device, need, "metrics")
     with torch.cuda.device(topk.device):
+        ev = _prof_begin()
         _lib.check(lib.gmr_hits_metrics(_ptr(topk), _ptr(gt_rowptr.contiguous()), _ptr(gt_items.contiguous()), u, k,
                                         _ptr(hit), _ptr(sums), _ptr(ws), need, _stream()), "gmr_hits_metrics")
+        _prof_end("hits_metrics", ev, users=u, k=k)
     LAUNCHES += 2
     return sums, hit

@@ -115,6 +115,12 @@ int gmr_score_mask_topk_f32(const float* Eu, int64_t lde_u, const int64_t* users
                             const int32_t* mask_items, int32_t K, int32_t precision, int32_t* out_ids,
                             float* out_scores, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Dense variant for API parity with full_sort_predict (GenMMRec/src/models/diffmm.py:277): writes the
+ * fp32 [B, I] score matrix (leading dimension ldo) with the same fmaf chain.  Not used by the fused
+ * evaluation. */
+int gmr_scores_f32(const float* Eu, int64_t lde_u, const int64_t* users, int32_t B, const float* Ei, int64_t lde_i,
+                   const float* bias, int32_t I, int32_t D, float* out, int64_t ldo, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K4  hit matrix + Recall / NDCG / Precision / MAP prefix sums
  * replaces  the Python membership loop and the numpy metric kernels
