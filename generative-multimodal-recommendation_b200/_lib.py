@@ -32,6 +32,7 @@ SIGNATURES = {
     "gmr_score_topk_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32, _i32]),
     "gmr_score_mask_topk_f32": (C.c_int, [_vp, _i64, _vp, _i32, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _i32, _i32, _vp,
                                           _vp, _vp, _i64, _vp]),
+    "gmr_score_tc_fallback_rows": (C.c_int, [_vp, _i32, _i32, _i32, _i32, C.POINTER(_i32), _vp]),
     "gmr_scores_f32": (C.c_int, [_vp, _i64, _vp, _i32, _vp, _i64, _vp, _i32, _i32, _vp, _i64, _vp]),
     "gmr_hits_metrics_workspace_bytes": (_i64, [_i32, _i32]),
     "gmr_hits_metrics": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),

@@ -45,6 +45,9 @@ int score_topk_tc_launch(const float* Eu, int64_t lde_u, const int64_t* users, i
                          const int32_t* mask_items, int32_t K, int32_t* out_ids, float* out_scores, void* workspace,
                          int64_t workspace_bytes, cudaStream_t st);
 
+int score_tc_fallback_count(const void* workspace, int32_t B, int32_t I, int32_t D, int32_t K, int32_t* count_host,
+                            cudaStream_t st);
+
 }  // namespace gmr
 
 extern "C" const char* gmr_last_error(void) { return gmr::g_err; }
@@ -106,7 +109,7 @@ extern "C" int gmr_score_mask_topk_f32(const float* Eu, int64_t lde_u, const int
     cudaStream_t st = (cudaStream_t)stream;
     if (precision == GMR_SCORE_TC) {
         if (!gmr::score_tc_supported(D, K)) {
-            gmr::set_error("gmr_score_mask_topk_f32: GMR_SCORE_TC needs D %% 16 == 0, 16 <= D <= 256 (got D=%d)", D);
+            gmr::set_error("gmr_score_mask_topk_f32: GMR_SCORE_TC needs D %% 64 == 0, D <= 256 and K <= 248 (got D=%d, K=%d)", D, K);
             return GMR_ERR_UNSUPPORTED;
         }
         return gmr::score_topk_tc_launch(Eu, lde_u, users, B, Ei, lde_i, bias, I, D, mask_rowptr, mask_items, K,
@@ -114,6 +117,17 @@ extern "C" int gmr_score_mask_topk_f32(const float* Eu, int64_t lde_u, const int
     }
     return gmr::score_topk_simt_launch(Eu, lde_u, users, nullptr, B, Ei, lde_i, bias, I, D, mask_rowptr, mask_items,
                                        K, out_ids, out_scores, workspace, st, 0);
+}
+
+extern "C" int gmr_score_tc_fallback_rows(const void* workspace, int32_t B, int32_t I, int32_t D, int32_t K,
+                                          int32_t* count_host, void* stream)
+{
+    GMR_REQUIRE(workspace && count_host, "gmr_score_tc_fallback_rows: null argument");
+    if (!gmr::score_tc_supported(D, K)) {
+        *count_host = 0;
+        return GMR_OK;
+    }
+    return gmr::score_tc_fallback_count(workspace, B, I, D, K, count_host, (cudaStream_t)stream);
 }
 
 extern "C" int gmr_scores_f32(const float* Eu, int64_t lde_u, const int64_t* users, int32_t B, const float* Ei,

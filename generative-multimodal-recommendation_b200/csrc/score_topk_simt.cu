@@ -29,6 +29,7 @@ struct ScoreArgs {
     const int64_t* users;   // or null
     const int32_t* row_map; // or null: tile row -> batch row (exact re-run of selected rows)
     int32_t B;              // rows processed by this launch (length of row_map when given)
+    const int32_t* B_dev;   // or null: the row count lives on the device (rows queued by the tensor-core path)
     const float* Ei;
     int64_t lde_i;
     const float* bias;
@@ -55,7 +56,8 @@ __global__ void __launch_bounds__(kThreads, 2) score_topk_simt_kernel(ScoreArgs 
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int tx = t & 15, ty = t >> 4;
-    const int n_utiles = (a.B + kBU - 1) / kBU;
+    const int n_rows = a.B_dev ? min(*a.B_dev, a.B) : a.B;
+    const int n_utiles = (n_rows + kBU - 1) / kBU;
     const int n_itiles = (a.I + kBI - 1) / kBI;
     const int n_chunks = (a.D + kDK - 1) / kDK;
     uint64_t* my_slots = a.slots + (int64_t)blockIdx.x * kBU * CAP;
@@ -70,7 +72,7 @@ __global__ void __launch_bounds__(kThreads, 2) score_topk_simt_kernel(ScoreArgs 
         __syncthreads();  // previous tile fully retired
         if (t < kBU) {
             const int r = u0 + t;
-            row_b[t] = (r < a.B) ? (a.row_map ? a.row_map[r] : r) : -1;
+            row_b[t] = (r < n_rows) ? (a.row_map ? a.row_map[r] : r) : -1;
             rows[t].cnt = 0;
             rows[t].thr_score = -INFINITY;
             rows[t].thr_key = 0ull;
@@ -326,6 +328,9 @@ static int simt_grid(int32_t B)
     return tiles < 2 * sm_count() ? tiles : 2 * sm_count();
 }
 
+static thread_local const int32_t* g_dynamic_rows = nullptr;
+void score_simt_set_dynamic_rows(const int32_t* n_rows_dev) { g_dynamic_rows = n_rows_dev; }
+
 static int npl_for(int32_t K) { return K <= 64 ? 8 : (K <= 128 ? 16 : 32); }
 
 int64_t score_simt_workspace_bytes(int32_t B, int32_t K)
@@ -342,7 +347,7 @@ int score_topk_simt_launch(const float* Eu, int64_t lde_u, const int64_t* users,
 {
     if (n_rows == 0) return GMR_OK;
     ScoreArgs a;
-    a.Eu = Eu; a.lde_u = lde_u; a.users = users; a.row_map = row_map; a.B = n_rows;
+    a.Eu = Eu; a.lde_u = lde_u; a.users = users; a.row_map = row_map; a.B = n_rows; a.B_dev = g_dynamic_rows;
     a.Ei = Ei; a.lde_i = lde_i; a.bias = bias; a.I = I; a.D = D;
     a.mask_rowptr = mask_rowptr; a.mask_items = mask_items; a.K = K;
     a.out_ids = out_ids; a.out_scores = out_scores; a.slots = (uint64_t*)workspace;

@@ -1,16 +1,635 @@
-// score_topk_tc.cu -- K2/K3 (tensor-core path) -- placeholder until the tcgen05 kernel lands.
+// score_topk_tc.cu -- K2 + K3: fused score + mask + top-K with the dense contraction on the 5th-gen
+// tensor cores (tcgen05.mma, TMEM accumulators, TMA-fed operands), sm_100a only.
+//
+// Replaces the same reference call chain as score_topk_simt.cu
+//   torch.matmul(u_e[user], i_e.T) -> scores[mask] = -1e10 -> torch.topk   (models/diffmm.py:276-278,
+//   common/trainer.py:381-386) and returns THE SAME ids/scores as the fp32 path:
+//
+//   1. split: every fp32 operand x is written as bf16 terms hi = bf16(x), mid = bf16(x - hi).  With
+//      A' = [hi | hi | mid] (users) and B' = [hi | mid | hi] (items) along K, one bf16 GEMM over
+//      K' = 3 D yields  hi.hi + hi.mid + mid.hi,  i.e. the fp32 product up to
+//      |err| <= kSplitErr * |u|_2 * max_i |e_i|_2  (the dropped terms are O(2^-16) relative).
+//   2. a persistent, warp-specialised CTA per 128-user tile sweeps all item tiles:
+//        warp 0   TMA producer   (cp.async.bulk.tensor, 128B-swizzled K-major tiles, mbarrier tx)
+//        warp 1   MMA issuer     (one elected thread: 3*D/16 tcgen05.mma per 128 x 128 tile into a
+//                                 double-buffered TMEM accumulator; tcgen05.commit -> mbarriers)
+//        warps 2-5 epilogue      (tcgen05.ld 32 lanes x 32 columns; thread = user row: bias, running
+//                                 threshold filter, mask lookup only for survivors, append to the
+//                                 row's key slots; warp-cooperative bitonic compaction)
+//      The [B, I] score matrix exists only as 128 x 128 fp32 tiles in TMEM.
+//   3. at the end of a user tile the epilogue warps re-score the KP >= K + 8 surviving candidates of
+//      each row with the exact fp32 fmaf chain, sort them by (score desc, id asc) and write the top K.
+//      A row is CERTIFIED exact when  t + eps < s_K  (t = approximate score of its weakest kept
+//      candidate, eps the bound above, s_K its K-th exact score): no item outside the candidate list
+//      can then reach the top K.  Uncertified rows (rare: needs >= KP - K near-ties) are queued
+//      and redone by the fp32 kernel, so both precision modes return identical results.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
 #include "common.cuh"
+#include "topk_select.cuh"
 
 namespace gmr {
 
-bool score_tc_supported(int32_t, int32_t) { return false; }
-int64_t score_tc_workspace_bytes(int32_t, int32_t, int32_t, int32_t) { return 0; }
-int score_topk_tc_launch(const float*, int64_t, const int64_t*, int32_t, const float*, int64_t, const float*, int32_t,
-                         int32_t, const int64_t*, const int32_t*, int32_t, int32_t*, float*, void*, int64_t,
-                         cudaStream_t)
+// fp32 kernel entry used for the uncertified rows (score_topk_simt.cu)
+int score_topk_simt_launch(const float* Eu, int64_t lde_u, const int64_t* users, const int32_t* row_map,
+                           int32_t n_rows, const float* Ei, int64_t lde_i, const float* bias, int32_t I, int32_t D,
+                           const int64_t* mask_rowptr, const int32_t* mask_items, int32_t K, int32_t* out_ids,
+                           float* out_scores, void* workspace, cudaStream_t st, int grid_override);
+int64_t score_simt_workspace_bytes(int32_t B, int32_t K);
+void score_simt_set_dynamic_rows(const int32_t* n_rows_dev);
+
+constexpr int kTM = 128;          // users per tile (UMMA M)
+constexpr int kTN = 128;          // items per tile (UMMA N)
+constexpr int kMaxStages = 12;    // B' K-atom ring (as many 16 KB stages as fit beside the A' tile)
+constexpr int kTcThreads = 192;   // 6 warps
+constexpr float kSplitErr = 6.2e-5f;  // 3 * 2^-16 (dropped split terms) + fp32 accumulation slack
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
 {
-    set_error("tensor-core scoring path not built");
-    return GMR_ERR_UNSUPPORTED;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile (rows x 64 bf16 per 128-byte row, 8-row swizzle atoms of
+// 1024 B): start address >> 4, LBO = 1 (unused for swizzled K-major), SBO = 1024 B, version 1
+// (Blackwell), layout type 2 (SWIZZLE_128B).  Field layout: cute/arch/mma_sm100_desc.hpp.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr)
+{
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, M x N
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---- 1. operand split -----------------------------------------------------------------------------
+// out[r, :] = [hi | hi | mid] (is_a) or [hi | mid | hi] over 3 * D bf16; rows >= n_rows are zero.
+__global__ void __launch_bounds__(256)
+    split_bf16_kernel(const float* __restrict__ E, int64_t lde, const int64_t* __restrict__ rows, int32_t n_rows,
+                      int32_t n_rows_pad, int32_t D, int is_a, __nv_bfloat16* __restrict__ out,
+                      float* __restrict__ row_norm, uint32_t* __restrict__ max_norm_bits)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n_rows_pad) return;
+    __nv_bfloat16* o = out + r * (3 * (int64_t)D);
+    float ss = 0.f;
+    for (int d = lane; d < D; d += 32) {
+        float x = 0.f;
+        if (r < n_rows) x = E[(rows ? rows[r] : r) * lde + d];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+        const __nv_bfloat16 mid = __float2bfloat16_rn(x - __bfloat162float(hi));
+        o[d] = hi;
+        o[D + d] = is_a ? hi : mid;
+        o[2 * D + d] = is_a ? mid : hi;
+        ss = fmaf(x, x, ss);
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, m);
+    if (lane == 0) {
+        const float nrm = sqrtf(ss) * 1.0000002f;  // round up: this feeds an error BOUND
+        if (row_norm != nullptr && r < n_rows) row_norm[r] = nrm;
+        if (max_norm_bits != nullptr) atomicMax(max_norm_bits, __float_as_uint(nrm));
+    }
+}
+
+// ---- 2. + 3. the fused kernel ---------------------------------------------------------------------
+struct TcArgs {
+    const float* Eu;
+    int64_t lde_u;
+    const int64_t* users;
+    int32_t B;
+    const float* Ei;
+    int64_t lde_i;
+    const float* bias;
+    int32_t I, D;
+    const int64_t* mask_rowptr;
+    const int32_t* mask_items;
+    int32_t K;
+    int32_t* out_ids;
+    float* out_scores;
+    uint64_t* slots;          // [grid][kTM][CAP]
+    const float* a_norm;      // [B]
+    const uint32_t* b_max_norm_bits;
+    int32_t* fallback_rows;   // [B]
+    int32_t* fallback_count;  // [1]
+    int32_t n_stages;
+};
+
+// dynamic shared memory layout (1024-byte aligned): A' atoms (resident per user tile) | ring of B'
+// atoms (one 128 x 64 bf16 K-atom = 16 KB per stage) | bias tile | barriers | row states
+template <int NPL>
+__global__ void __launch_bounds__(kTcThreads, 1)
+    score_topk_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcArgs a)
+{
+    constexpr int CAP = 32 * NPL;
+    constexpr int KP = CAP / 4;
+    constexpr int TRIG = CAP - 32;
+
+    extern __shared__ uint8_t smem_dyn[];
+    uint8_t* smem_raw = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    const int n_atoms = (3 * a.D) / 64;                       // K' / 64
+    const int n_stages = a.n_stages;
+    const uint32_t atom_a_bytes = kTM * 128, atom_b_bytes = kTN * 128;
+    uint8_t* sm_a = smem_raw;
+    uint8_t* sm_b = sm_a + (size_t)n_atoms * atom_a_bytes;    // [n_stages][kTN * 128 B]
+    uint8_t* tail = sm_b + (size_t)n_stages * atom_b_bytes;
+    float* sm_bias = reinterpret_cast<float*>(tail);          // [2][kTN]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 2 * kTN * sizeof(float));
+    uint64_t* full_b = bars;                    // [kMaxStages]
+    uint64_t* empty_b = bars + kMaxStages;      // [kMaxStages]
+    uint64_t* tmem_full = bars + 2 * kMaxStages;      // [2]
+    uint64_t* tmem_empty = bars + 2 * kMaxStages + 2; // [2]
+    uint64_t* a_full = bars + 2 * kMaxStages + 4;
+    uint64_t* a_empty = bars + 2 * kMaxStages + 5;
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 6);
+    RowState* rows = reinterpret_cast<RowState*>(bars + 2 * kMaxStages + 8);  // [kTM]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_utiles = (a.B + kTM - 1) / kTM;
+    const int n_itiles = (a.I + kTN - 1) / kTN;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < n_stages; ++s) {
+            mbar_init(&full_b[s], 1);
+            mbar_init(&empty_b[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tmem_full[s], 1);
+            mbar_init(&tmem_empty[s], 128);
+        }
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
+                     "r"(2 * kTN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, a_phase = 0;
+            for (int ut = blockIdx.x; ut < n_utiles; ut += gridDim.x) {
+                mbar_wait(a_empty, a_phase ^ 1);  // first pass: passes immediately (fresh barrier)
+                mbar_expect_tx(a_full, (uint32_t)n_atoms * atom_a_bytes);
+                for (int k = 0; k < n_atoms; ++k) tma_load_2d(sm_a + (size_t)k * atom_a_bytes, &map_a, a_full, k * 64, ut * kTM);
+                a_phase ^= 1;
+                for (int it = 0; it < n_itiles; ++it) {
+                    for (int k = 0; k < n_atoms; ++k) {
+                        mbar_wait(&empty_b[stage], phase ^ 1);
+                        mbar_expect_tx(&full_b[stage], atom_b_bytes);
+                        tma_load_2d(sm_b + (size_t)stage * atom_b_bytes, &map_b, &full_b[stage], k * 64, it * kTN);
+                        if (++stage == n_stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one elected thread) =====
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(kTM, kTN);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0, a_phase = 0;
+            for (int ut = blockIdx.x; ut < n_utiles; ut += gridDim.x) {
+                mbar_wait(a_full, a_phase);
+                a_phase ^= 1;
+                for (int it = 0; it < n_itiles; ++it) {
+                    mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)acc * kTN;
+                    const uint32_t a_base = smem_u32(sm_a);
+                    for (int k = 0; k < n_atoms; ++k) {
+                        mbar_wait(&full_b[stage], phase);
+                        tc_fence_after();
+                        const uint32_t b_base = smem_u32(sm_b + (size_t)stage * atom_b_bytes);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {  // 4 x (K = 16 bf16 = 32 B) per 128-byte swizzle row
+                            const uint64_t ad = umma_desc_sw128(a_base + k * atom_a_bytes + kk * 32);
+                            const uint64_t bd = umma_desc_sw128(b_base + kk * 32);
+                            tc_mma_bf16(d_tmem, ad, bd, idesc, (k | kk) ? 1u : 0u);
+                        }
+                        tc_commit(&empty_b[stage]);  // this B' atom may be overwritten once its MMAs retire
+                        if (++stage == n_stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    tc_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+                    if (++acc == 2) {
+                        acc = 0;
+                        acc_phase ^= 1;
+                    }
+                }
+                tc_commit(a_empty);  // A' tile free once every MMA of this user tile retired
+            }
+        }
+    } else {
+        // ===== epilogue: thread = user row (TMEM lane), warps 2..5 own lane quarters (warp % 4) =====
+        const int q = warp & 3;
+        const int row = q * 32 + lane;  // row inside the user tile == TMEM lane
+        uint64_t* cta_slots = a.slots + (int64_t)blockIdx.x * kTM * CAP;
+        uint64_t* my_slots = cta_slots + (int64_t)row * CAP;
+        RowState* st = &rows[row];
+        const int et = threadIdx.x - 64;  // 0..127 among epilogue threads
+        const float b_max = __uint_as_float(*a.b_max_norm_bits);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int ut = blockIdx.x; ut < n_utiles; ut += gridDim.x) {
+            const int b = ut * kTM + row;
+            const bool valid = b < a.B;
+            int64_t mlo = 0, mhi = 0;
+            if (valid && a.mask_rowptr != nullptr) {
+                mlo = a.mask_rowptr[b];
+                mhi = a.mask_rowptr[b + 1];
+            }
+            int cnt = 0;
+            float thr = -INFINITY;
+            uint64_t thr_key = 0ull;
+            st->cnt = 0;
+            st->thr_score = -INFINITY;
+            st->thr_key = 0ull;
+            __syncwarp();
+
+            for (int it = 0; it < n_itiles; ++it) {
+                const int i0 = it * kTN;
+                if (a.bias != nullptr) {
+                    // stage the bias tile (double-buffered with the accumulator) and sync the 4 warps
+                    sm_bias[acc * kTN + et] = (i0 + et < a.I) ? a.bias[i0 + et] : 0.f;
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * kTN;
+#pragma unroll 1
+                for (int c0 = 0; c0 < kTN; c0 += 32) {
+                    uint32_t v[32];
+                    tc_ld_32x32(taddr + c0, v);
+                    float mx = -INFINITY;
+                    if (a.bias != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float s = __uint_as_float(v[j]) + sm_bias[acc * kTN + c0 + j];
+                            v[j] = __float_as_uint(s);
+                            mx = fmaxf(mx, s);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+                    }
+                    if (valid && mx >= thr) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float s = __uint_as_float(v[j]);
+                            if (s >= thr) {
+                                const int item = i0 + c0 + j;
+                                if (item < a.I) {
+                                    if (mlo != mhi && sorted_contains(a.mask_items, mlo, mhi, item)) s = -1e10f;
+                                    const uint64_t key = make_key(s, item);
+                                    if (key > thr_key) my_slots[cnt++] = key;
+                                }
+                            }
+                        }
+                    }
+                    // warp-cooperative compaction of the rows that are about to run out of slots
+                    unsigned need = __ballot_sync(0xffffffffu, cnt >= TRIG);
+                    if (need) {
+                        st->cnt = cnt;
+                        __syncwarp();
+                        while (need) {
+                            const int l = __ffs(need) - 1;
+                            need &= need - 1;
+                            compact_row<NPL>(cta_slots + (int64_t)(q * 32 + l) * CAP, &rows[q * 32 + l], KP - 1, lane);
+                        }
+                        cnt = st->cnt;
+                        thr = st->thr_score;
+                        thr_key = st->thr_key;
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&tmem_empty[acc]);
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+
+            // ---- user tile done: exact re-score, sort, certify, write (warp handles its 32 rows) ----
+            st->cnt = cnt;
+            __syncwarp();
+            for (int l = 0; l < 32; ++l) {
+                const int r = q * 32 + l;
+                const int rb = ut * kTM + r;
+                if (rb >= a.B) break;  // rows are contiguous: warp-uniform exit
+                uint64_t* s_row = cta_slots + (int64_t)r * CAP;
+                compact_row<NPL>(s_row, &rows[r], KP - 1, lane);
+                const int n_cand = rows[r].cnt;  // <= KP, sorted by approximate key
+                const float t_approx = (n_cand >= KP) ? key_score(s_row[KP - 1]) : -INFINITY;
+                const float* u = a.Eu + (a.users ? a.users[rb] : (int64_t)rb) * a.lde_u;
+                uint64_t ek[NPL / 4];
+#pragma unroll
+                for (int c = 0; c < NPL / 4; ++c) {
+                    const int j = c * 32 + lane;
+                    uint64_t key = 0ull;
+                    if (j < n_cand) {
+                        const uint64_t ak = s_row[j];
+                        const int item = key_id(ak);
+                        float s;
+                        if (key_score(ak) == -1e10f) {
+                            s = -1e10f;  // masked (trainer.py:384): exact by definition
+                        } else {
+                            const float* e = a.Ei + (int64_t)item * a.lde_i;
+                            s = a.bias ? a.bias[item] : 0.f;
+                            for (int d = 0; d < a.D; ++d) s = fmaf(u[d], e[d], s);
+                        }
+                        key = make_key(s, item);
+                    }
+                    ek[c] = key;
+                }
+                warp_bitonic_sort_desc<NPL / 4>(ek, lane);
+                // K-th exact key -> certification
+                const int kth = a.K - 1;
+                uint64_t kth_key = 0ull;
+#pragma unroll
+                for (int c = 0; c < NPL / 4; ++c) {
+                    const uint64_t cand = __shfl_sync(0xffffffffu, ek[c], kth & 31);
+                    if (c == (kth >> 5)) kth_key = cand;
+                }
+                bool certified = true;
+                if (n_cand >= KP) {  // otherwise every item that could matter is in the list
+                    const float eps = kSplitErr * a.a_norm[rb] * b_max + 4.8e-7f * fabsf(t_approx);
+                    certified = (kth_key != 0ull) && (t_approx + eps < key_score(kth_key));
+                }
+#pragma unroll
+                for (int c = 0; c < NPL / 4; ++c) {
+                    const int j = c * 32 + lane;
+                    if (j < a.K) {
+                        const bool ok = ek[c] != 0ull;
+                        a.out_ids[(int64_t)rb * a.K + j] = ok ? key_id(ek[c]) : -1;
+                        if (a.out_scores) a.out_scores[(int64_t)rb * a.K + j] = ok ? key_score(ek[c]) : -INFINITY;
+                    }
+                }
+                if (!certified && lane == 0) a.fallback_rows[atomicAdd(a.fallback_count, 1)] = rb;
+            }
+            __syncwarp();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * kTN) : "memory");
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// [rows, kd] bf16 row-major, boxes of 64 (K) x box_rows, 128-byte swizzle
+static bool make_map(CUtensorMap* m, void* base, int64_t rows, int64_t kd, int box_rows)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (fn == nullptr) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)kd, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)kd * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int tc_stages_for(int32_t D);
+static int tc_kp(int32_t K) { return K + 8 <= 64 ? 64 : (K + 8 <= 128 ? 128 : 256); }
+
+bool score_tc_supported(int32_t D, int32_t K) { return D % 64 == 0 && D >= 64 && D <= 256 && K + 8 <= 256 && tc_stages_for(D) >= 2; }
+
+static int tc_grid(int32_t B)
+{
+    const int tiles = (B + kTM - 1) / kTM;
+    return tiles < sm_count() ? tiles : sm_count();
+}
+
+struct TcLayout {
+    int64_t a_split, b_split, a_norm, misc, fallback, slots, simt, total;
+    int32_t b_pad, i_pad;
+};
+
+static TcLayout tc_layout(int32_t B, int32_t I, int32_t D, int32_t K)
+{
+    TcLayout L;
+    L.b_pad = (B + kTM - 1) / kTM * kTM;
+    L.i_pad = (I + kTN - 1) / kTN * kTN;
+    const int cap = 4 * tc_kp(K);
+    int64_t off = 0;
+    auto take = [&](int64_t bytes) {
+        const int64_t o = off;
+        off += align_up(bytes, 256);
+        return o;
+    };
+    L.a_split = take((int64_t)L.b_pad * 3 * D * 2);
+    L.b_split = take((int64_t)L.i_pad * 3 * D * 2);
+    L.a_norm = take((int64_t)L.b_pad * 4);
+    L.misc = take(256);  // [0] max item norm bits, [1] fallback count
+    L.fallback = take((int64_t)B * 4);
+    L.slots = take((int64_t)tc_grid(B) * kTM * cap * 8);
+    L.simt = take(score_simt_workspace_bytes(B, K));
+    L.total = off;
+    return L;
+}
+
+int64_t score_tc_workspace_bytes(int32_t B, int32_t I, int32_t D, int32_t K) { return tc_layout(B, I, D, K).total; }
+
+
+static size_t tc_smem_fixed(int32_t D)
+{
+    const int n_atoms = 3 * D / 64;
+    return (size_t)n_atoms * kTM * 128 + 2 * kTN * sizeof(float) + (2 * kMaxStages + 8) * sizeof(uint64_t) +
+           kTM * sizeof(RowState) + 1024;
+}
+static int tc_stages(int32_t D)
+{
+    const int64_t room = (int64_t)227 * 1024 - (int64_t)tc_smem_fixed(D);
+    const int s = (int)(room / (kTN * 128));
+    return s > kMaxStages ? kMaxStages : s;
+}
+
+static int tc_stages_for(int32_t D) { return tc_stages(D); }
+
+// rows the last tensor-core call could not certify (they were redone on the fp32 path); synchronises
+int score_tc_fallback_count(const void* workspace, int32_t B, int32_t I, int32_t D, int32_t K, int32_t* count_host,
+                            cudaStream_t st)
+{
+    const TcLayout L = tc_layout(B, I, D, K);
+    GMR_CHECK_CUDA(cudaMemcpyAsync(count_host, (const uint8_t*)workspace + L.misc + 4, sizeof(int32_t),
+                                   cudaMemcpyDeviceToHost, st));
+    GMR_CHECK_CUDA(cudaStreamSynchronize(st));
+    return GMR_OK;
+}
+
+int score_topk_tc_launch(const float* Eu, int64_t lde_u, const int64_t* users, int32_t B, const float* Ei,
+                         int64_t lde_i, const float* bias, int32_t I, int32_t D, const int64_t* mask_rowptr,
+                         const int32_t* mask_items, int32_t K, int32_t* out_ids, float* out_scores, void* workspace,
+                         int64_t workspace_bytes, cudaStream_t st)
+{
+    const TcLayout L = tc_layout(B, I, D, K);
+    if (workspace_bytes < L.total) {
+        set_error("score_topk_tc: workspace of %lld bytes required, %lld given", (long long)L.total, (long long)workspace_bytes);
+        return GMR_ERR_WORKSPACE;
+    }
+    if ((uintptr_t)workspace % 256 != 0) {
+        set_error("score_topk_tc: workspace must be 256-byte aligned");
+        return GMR_ERR_INVALID;
+    }
+    const int n_stages = tc_stages(D);
+    if (n_stages < 2) {
+        set_error("score_topk_tc: D=%d leaves no room for the operand ring in shared memory", D);
+        return GMR_ERR_UNSUPPORTED;
+    }
+    const size_t smem = tc_smem_fixed(D) + (size_t)n_stages * kTN * 128;
+    uint8_t* ws = (uint8_t*)workspace;
+    __nv_bfloat16* a_split = (__nv_bfloat16*)(ws + L.a_split);
+    __nv_bfloat16* b_split = (__nv_bfloat16*)(ws + L.b_split);
+    float* a_norm = (float*)(ws + L.a_norm);
+    uint32_t* misc = (uint32_t*)(ws + L.misc);
+    int32_t* fallback = (int32_t*)(ws + L.fallback);
+
+    GMR_CHECK_CUDA(cudaMemsetAsync(misc, 0, 256, st));
+    const int wpb = 8;
+    split_bf16_kernel<<<(L.b_pad + wpb - 1) / wpb, wpb * 32, 0, st>>>(Eu, lde_u, users, B, L.b_pad, D, 1, a_split, a_norm, nullptr);
+    GMR_LAUNCH_CHECK();
+    split_bf16_kernel<<<(L.i_pad + wpb - 1) / wpb, wpb * 32, 0, st>>>(Ei, lde_i, nullptr, I, L.i_pad, D, 0, b_split, nullptr, misc);
+    GMR_LAUNCH_CHECK();
+
+    CUtensorMap map_a, map_b;
+    if (!make_map(&map_a, a_split, L.b_pad, 3 * (int64_t)D, kTM) || !make_map(&map_b, b_split, L.i_pad, 3 * (int64_t)D, kTN)) {
+        set_error("score_topk_tc: cuTensorMapEncodeTiled unavailable or failed");
+        return GMR_ERR_CUDA;
+    }
+    TcArgs a;
+    a.Eu = Eu; a.lde_u = lde_u; a.users = users; a.B = B; a.Ei = Ei; a.lde_i = lde_i; a.bias = bias; a.I = I; a.D = D;
+    a.mask_rowptr = mask_rowptr; a.mask_items = mask_items; a.K = K; a.out_ids = out_ids; a.out_scores = out_scores;
+    a.slots = (uint64_t*)(ws + L.slots); a.a_norm = a_norm; a.b_max_norm_bits = misc;
+    a.fallback_rows = fallback; a.fallback_count = (int32_t*)(misc + 1); a.n_stages = n_stages;
+    const int grid = tc_grid(B);
+    const int kp = tc_kp(K);
+#define GMR_TC_LAUNCH(NPL)                                                                                         \
+    do {                                                                                                           \
+        GMR_CHECK_CUDA(cudaFuncSetAttribute(score_topk_tc_kernel<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                            (int)smem));                                                           \
+        score_topk_tc_kernel<NPL><<<grid, kTcThreads, smem, st>>>(map_a, map_b, a);                                \
+    } while (0)
+    if (kp == 64)
+        GMR_TC_LAUNCH(8);
+    else if (kp == 128)
+        GMR_TC_LAUNCH(16);
+    else
+        GMR_TC_LAUNCH(32);
+#undef GMR_TC_LAUNCH
+    GMR_LAUNCH_CHECK();
+    // uncertified rows: exact fp32 kernel, row count read on the device (no host synchronisation)
+    score_simt_set_dynamic_rows((const int32_t*)(misc + 1));
+    const int fb_grid = 2 * sm_count() < (B + 127) / 128 ? 2 * sm_count() : (B + 127) / 128;
+    int rc = score_topk_simt_launch(Eu, lde_u, users, fallback, B, Ei, lde_i, bias, I, D, mask_rowptr, mask_items, K,
+                                    out_ids, out_scores, ws + L.simt, st, fb_grid);
+    score_simt_set_dynamic_rows(nullptr);
+    return rc;
 }
 
 }  // namespace gmr

@@ -238,6 +238,11 @@ def rows_axpby_norm(x, y=None, z=None, a=1.0, b=0.0, c=0.0, eps=1e-12, out=None)
     return out
 
 
+def tc_supported(d, k):
+    """Shapes the tcgen05 scoring path accepts (A' tile + >= 2 ring stages must fit in shared memory)."""
+    return d % 64 == 0 and 64 <= d <= 192 and k <= 248
+
+
 def score_mask_topk(eu, ei, k, users=None, bias=None, mask_rowptr=None, mask_items=None, precision="fp32",
                     return_scores=True):
     """Fused full-sort scoring + train-history mask + top-K (K2).
@@ -248,6 +253,8 @@ def score_mask_topk(eu, ei, k, users=None, bias=None, mask_rowptr=None, mask_ite
     """
     global LAUNCHES
     lib = _lib.load()
+    if precision == "auto":  # tensor cores whenever the shape is supported; both paths return the same result
+        precision = "tc" if tc_supported(int(ei.shape[1]), k) else "fp32"
     mode = {"fp32": _lib.GMR_SCORE_FP32, "tc": _lib.GMR_SCORE_TC}[precision]
     eup, lde_u = _rows(eu, "eu")
     eip, lde_i = _rows(ei, "ei")
@@ -274,8 +281,25 @@ def score_mask_topk(eu, ei, k, users=None, bias=None, mask_rowptr=None, mask_ite
                                                _ptr(mask_rowptr), _ptr(mask_items), k, mode, _ptr(ids), _ptr(scores),
                                                _ptr(ws), need, _stream()), "gmr_score_mask_topk_f32")
         _prof_end("score_topk", ev, flops=2.0 * b * i * d, users=b, items=i, d=d, k=k, precision=precision)
-    LAUNCHES += 1
+    LAUNCHES += 1 if mode == _lib.GMR_SCORE_FP32 else 4  # tc: 2 split kernels + fused kernel + fp32 redo
+    global _last_score_call
+    _last_score_call = (ws, b, i, d, k, mode)
     return ids, scores
+
+
+_last_score_call = None
+
+
+def last_tc_fallback_rows():
+    """Rows of the most recent ``precision='tc'`` call that were redone on the exact fp32 path because
+    their candidate margin could not certify exactness (diagnostic; synchronises)."""
+    if _last_score_call is None or _last_score_call[5] != _lib.GMR_SCORE_TC:
+        return 0
+    ws, b, i, d, k, _ = _last_score_call
+    out = C.c_int32(0)
+    _lib.check(_lib.load().gmr_score_tc_fallback_rows(_ptr(ws), b, i, d, k, C.byref(out), _stream()),
+               "gmr_score_tc_fallback_rows")
+    return int(out.value)
 
 
 def scores_dense(eu, ei, users=None, bias=None):

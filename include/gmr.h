@@ -102,7 +102,7 @@ int gmr_spmm_csr_f32_push(const gmr_spmm_plan_t* plan, const int32_t* rowptr, co
  *               GMR_SCORE_TC      tcgen05 split-bf16 scoring + exact fp32 re-scoring of the K'
  *                                 best candidates; rows whose candidate margin cannot certify
  *                                 exactness are redone on the fp32 path, so both modes return the
- *                                 same ids.  Requires D % 16 == 0, D <= 256.
+ *                                 same ids.  Requires D % 64 == 0, D <= 256, K <= 248.
  * 1 <= K <= GMR_MAX_TOPK; if fewer than K items exist the tail is (-1, -inf).
  * ------------------------------------------------------------------------------------------- */
 #define GMR_SCORE_FP32 0
@@ -114,6 +114,12 @@ int gmr_score_mask_topk_f32(const float* Eu, int64_t lde_u, const int64_t* users
                             int64_t lde_i, const float* bias, int32_t I, int32_t D, const int64_t* mask_rowptr,
                             const int32_t* mask_items, int32_t K, int32_t precision, int32_t* out_ids,
                             float* out_scores, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Diagnostics of the last GMR_SCORE_TC call that used `workspace` with the same shape: number of rows
+ * whose exactness could not be certified from the candidate margin (they were redone on the fp32
+ * path).  Copies one int to the host and synchronises `stream`. */
+int gmr_score_tc_fallback_rows(const void* workspace, int32_t B, int32_t I, int32_t D, int32_t K,
+                               int32_t* count_host, void* stream);
 
 /* Dense variant for API parity with full_sort_predict (GenMMRec/src/models/diffmm.py:277): writes the
  * fp32 [B, I] score matrix (leading dimension ldo) with the same fmaf chain.  Not used by the fused

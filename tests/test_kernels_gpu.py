@@ -198,3 +198,80 @@ def test_errors_are_loud(ops):
         ops.spmm_raw(g, torch.zeros((11, 64), device="cuda"))
     with pytest.raises(RuntimeError):
         ops.score_mask_topk(torch.zeros((4, 64), device="cuda"), torch.zeros((9, 64), device="cuda"), 1000)
+
+
+# ---- tensor-core scoring path (tcgen05 split-bf16 + exact re-rank): must equal the fp32 path ----------
+
+
+def _tc_case(ops, rng, n_users, b, n_items, d, k, with_bias, mask_avg, scale=1.0):
+    eu = (rng.standard_normal((n_users, d)) * scale).astype(np.float32)
+    ei = (rng.standard_normal((n_items, d)) * scale).astype(np.float32)
+    users = rng.choice(n_users, size=b, replace=False).astype(np.int64)
+    bias = rng.standard_normal(n_items).astype(np.float32) if with_bias else None
+    mrp, mit = make_mask(rng, b, n_items, mask_avg)
+    args = dict(users=torch.from_numpy(users).cuda(), bias=None if bias is None else torch.from_numpy(bias).cuda(),
+                mask_rowptr=torch.from_numpy(mrp).cuda(), mask_items=torch.from_numpy(mit).cuda())
+    eu_t, ei_t = torch.from_numpy(eu).cuda(), torch.from_numpy(ei).cuda()
+    ids_f, sc_f = ops.score_mask_topk(eu_t, ei_t, k, precision="fp32", **args)
+    ids_t, sc_t = ops.score_mask_topk(eu_t, ei_t, k, precision="tc", **args)
+    torch.cuda.synchronize()
+    return ids_f.cpu().numpy(), sc_f.cpu().numpy(), ids_t.cpu().numpy(), sc_t.cpu().numpy(), ops.last_tc_fallback_rows()
+
+
+@pytest.mark.parametrize("n_items,d,k,with_bias", [(7050, 64, 50, False), (1000, 64, 20, False), (333, 64, 5, True),
+                                                   (5000, 128, 50, False), (2100, 192, 50, True), (130, 64, 50, False),
+                                                   (4000, 64, 100, False), (3000, 128, 10, True)])
+def test_score_tc_equals_fp32(ops, n_items, d, k, with_bias):
+    rng = np.random.default_rng(1000 + n_items + d)
+    ids_f, sc_f, ids_t, sc_t, fb = _tc_case(ops, rng, 900, 517, n_items, d, k, with_bias, 25)
+    assert np.array_equal(ids_t, ids_f)
+    assert np.array_equal(sc_t, sc_f)
+    assert fb <= 0.02 * 517  # certification almost never fails on continuous random scores
+
+
+def test_score_tc_matches_oracle_bit_exact(ops):
+    rng = np.random.default_rng(77)
+    n_users, b, n_items, d, k = 400, 300, 2500, 64, 50
+    eu = rng.standard_normal((n_users, d)).astype(np.float32)
+    ei = rng.standard_normal((n_items, d)).astype(np.float32)
+    users = rng.choice(n_users, size=b, replace=False).astype(np.int64)
+    mrp, mit = make_mask(rng, b, n_items, 40)
+    ids_ref, sc_ref = c_api.score_mask_topk(eu, users, ei, None, mrp, mit, k)
+    ids, sc = ops.score_mask_topk(torch.from_numpy(eu).cuda(), torch.from_numpy(ei).cuda(), k,
+                                  users=torch.from_numpy(users).cuda(), mask_rowptr=torch.from_numpy(mrp).cuda(),
+                                  mask_items=torch.from_numpy(mit).cuda(), precision="tc")
+    assert np.array_equal(ids.cpu().numpy(), ids_ref)
+    assert np.array_equal(sc.cpu().numpy(), sc_ref)
+
+
+def test_score_tc_ties_force_exact_fallback(ops):
+    """Many duplicated items: near/exact ties everywhere, so certification must fail for most rows and
+    the fp32 redo must still deliver the oracle's total order (score desc, id asc)."""
+    rng = np.random.default_rng(5)
+    n_items, d, k = 1500, 64, 50
+    base = rng.standard_normal((30, d)).astype(np.float32)
+    ei = base[rng.integers(0, 30, size=n_items)]          # only 30 distinct item vectors
+    eu = rng.standard_normal((260, d)).astype(np.float32)
+    ids_ref, sc_ref = c_api.score_mask_topk(eu, None, ei, None, None, None, k)
+    ids, sc = ops.score_mask_topk(torch.from_numpy(eu).cuda(), torch.from_numpy(ei).cuda(), k, precision="tc")
+    fb = ops.last_tc_fallback_rows()
+    assert np.array_equal(ids.cpu().numpy(), ids_ref)
+    assert np.array_equal(sc.cpu().numpy(), sc_ref)
+    assert fb > 50  # certification fails wherever K-th/KP-th candidates are (near) ties
+
+
+def test_score_tc_wide_dynamic_range(ops):
+    """Rows and items with norms spread over 4 decades: the error bound scales with the norms."""
+    rng = np.random.default_rng(6)
+    n_items, d, k = 6000, 64, 50
+    eu = (rng.standard_normal((300, d)) * np.exp(rng.uniform(-4, 4, size=(300, 1)))).astype(np.float32)
+    ei = (rng.standard_normal((n_items, d)) * np.exp(rng.uniform(-4, 4, size=(n_items, 1)))).astype(np.float32)
+    ids_ref, sc_ref = c_api.score_mask_topk(eu, None, ei, None, None, None, k)
+    ids, sc = ops.score_mask_topk(torch.from_numpy(eu).cuda(), torch.from_numpy(ei).cuda(), k, precision="tc")
+    assert np.array_equal(ids.cpu().numpy(), ids_ref)
+    assert np.array_equal(sc.cpu().numpy(), sc_ref)
+
+
+def test_score_tc_unsupported_shapes_are_loud(ops):
+    with pytest.raises(RuntimeError):
+        ops.score_mask_topk(torch.zeros((4, 60), device="cuda"), torch.zeros((90, 60), device="cuda"), 5, precision="tc")

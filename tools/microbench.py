@@ -101,6 +101,14 @@ def main():
         fn = lambda: ops.score_mask_topk(ue, ie, args.k, users=users, mask_rowptr=mrp, mask_items=mit, precision="fp32")
         med, best = time_fn(fn, max(2, args.iters // 3), warmup=1)
         out["score_fp32"] = {"ms": med, "users_per_s": b / med * 1e3, "TFLOPs": 2.0 * b * ni * d / med / 1e9}
+        if ops.tc_supported(d, args.k):
+            fn = lambda: ops.score_mask_topk(ue, ie, args.k, users=users, mask_rowptr=mrp, mask_items=mit, precision="tc")
+            med, best = time_fn(fn, max(3, args.iters // 2), warmup=2)
+            out["score_tc"] = {"ms": med, "users_per_s": b / med * 1e3, "TFLOPs": 2.0 * b * ni * d / med / 1e9,
+                               "fallback_rows": ops.last_tc_fallback_rows()}
+            a = ops.score_mask_topk(ue, ie, args.k, users=users, mask_rowptr=mrp, mask_items=mit, precision="tc")
+            b2 = ops.score_mask_topk(ue, ie, args.k, users=users, mask_rowptr=mrp, mask_items=mit, precision="fp32")
+            out["score_tc_equals_fp32"] = bool(torch.equal(a[0], b2[0]) and torch.equal(a[1], b2[1]))
     print(json.dumps(out, indent=1))
 
 
