@@ -267,7 +267,8 @@ def run_gpu(args):
                 "frac": kernels[score_key]["alg_TFLOPs"] / tensor_peak, "traffic": None,
                 "peak_source": peaks["source"] + " bf16 sustained (kernel timed inside a long step)",
                 "share_of_step": score_share,
-                "note": "algorithmic flops 2*U*I*D; fp32 mode computes on CUDA cores (exact fmaf chain)"}
+                "note": "algorithmic flops 2*U*I*D (the tc mode issues 3x that many bf16 flops for the split-precision "
+                        "product; fp32 mode runs the exact fmaf chain on CUDA cores)"}
     roofline_spmm = {"kernel": big_spmm, "bound": "hbm", "achieved": kernels[big_spmm]["alg_GBs"],
                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": kernels[big_spmm]["alg_GBs"] / peaks["hbm_gbs"],
                      "traffic": None, "gather_model_GBs": kernels[big_spmm]["gather_GBs"],
@@ -408,7 +409,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="scaled", choices=sorted(WORKLOAD_NAMES))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("GMR_SCORE_PRECISION", "fp32"), choices=["fp32", "tc"])
+    ap.add_argument("--precision", default=os.environ.get("GMR_SCORE_PRECISION", "tc"), choices=["fp32", "tc"],
+                    help="scoring path: tc = tcgen05 split-bf16 + exact re-rank (same ids/scores as fp32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra-workloads", action="store_true")
     args = ap.parse_args()

@@ -58,7 +58,7 @@ class GeneralRecommender(AbstractRecommender):
         if self.device.type != "cuda":
             raise RuntimeError("genmmrec_b200 models run on CUDA only (device=%s): the hot path has no CPU "
                                "fallback" % self.device)
-        self.score_precision = config["score_precision"] or "fp32"
+        self.score_precision = config["score_precision"] or "auto"
         self.cache_propagation = config["cache_propagation"] is not False
 
         self.v_feat, self.t_feat = None, None

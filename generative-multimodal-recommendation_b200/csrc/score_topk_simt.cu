@@ -174,23 +174,7 @@ __global__ void __launch_bounds__(kThreads, 2) score_topk_simt_kernel(ScoreArgs 
                 const int item = i0 + (ii >> 2) * 64 + tx * 4 + (ii & 3);
                 if (item >= a.I) todo &= ~(0x0101010101010101ull << ii);
             }
-            // resolve masks once: masked pairs score exactly -1e10f (trainer.py:384)
-            if (todo != 0ull && a.mask_rowptr != nullptr) {
-#pragma unroll
-                for (int ui = 0; ui < 8; ++ui) {
-                    if (((todo >> (ui * 8)) & 0xFFull) == 0ull) continue;
-                    const int lr = (ui >> 2) * 64 + ty * 4 + (ui & 3);
-                    const int b = row_b[lr];
-                    const int64_t lo = a.mask_rowptr[b], hi = a.mask_rowptr[b + 1];
-                    if (lo == hi) continue;
-#pragma unroll
-                    for (int ii = 0; ii < 8; ++ii) {
-                        if (!((todo >> (ui * 8 + ii)) & 1ull)) continue;
-                        const int item = i0 + (ii >> 2) * 64 + tx * 4 + (ii & 3);
-                        if (sorted_contains(a.mask_items, lo, hi, item)) acc[ui][ii] = -1e10f;
-                    }
-                }
-            }
+            // the train-history mask is applied when a row is compacted (topk_select.cuh)
             while (true) {
                 if (todo != 0ull) {
 #pragma unroll
@@ -226,7 +210,12 @@ __global__ void __launch_bounds__(kThreads, 2) score_topk_simt_kernel(ScoreArgs 
                         const int l = __ffs(m) - 1;
                         m &= m - 1;
                         const int r = warp * 16 + l;
-                        compact_row<NPL>(my_slots + (int64_t)r * CAP, &rows[r], kth, lane);
+                        int64_t mlo = 0, mhi = 0;
+                        if (a.mask_rowptr != nullptr) {
+                            mlo = a.mask_rowptr[row_b[r]];
+                            mhi = a.mask_rowptr[row_b[r] + 1];
+                        }
+                        compact_row<NPL>(my_slots + (int64_t)r * CAP, &rows[r], kth, lane, a.mask_items, mlo, mhi);
                     }
                 }
                 __syncthreads();
@@ -239,7 +228,12 @@ __global__ void __launch_bounds__(kThreads, 2) score_topk_simt_kernel(ScoreArgs 
             const int b = row_b[r];
             if (b < 0) continue;
             uint64_t* s = my_slots + (int64_t)r * CAP;
-            compact_row<NPL>(s, &rows[r], kth, lane);
+            int64_t mlo = 0, mhi = 0;
+            if (a.mask_rowptr != nullptr) {
+                mlo = a.mask_rowptr[b];
+                mhi = a.mask_rowptr[b + 1];
+            }
+            compact_row<NPL>(s, &rows[r], kth, lane, a.mask_items, mlo, mhi);
             const int cnt = rows[r].cnt;
             for (int j = lane; j < a.K; j += 32) {
                 const bool ok = j < cnt;

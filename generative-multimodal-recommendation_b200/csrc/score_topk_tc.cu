@@ -26,6 +26,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "topk_select.cuh"
 
@@ -112,8 +114,8 @@ __device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile (rows x 64 bf16 per 128-byte row, 8-row swizzle atoms of
 // 1024 B): start address >> 4, LBO = 1 (unused for swizzled K-major), SBO = 1024 B, version 1
@@ -181,12 +183,14 @@ struct TcArgs {
     int32_t* fallback_rows;   // [B]
     int32_t* fallback_count;  // [1]
     int32_t n_stages;
+    uint32_t* dbg;  // misc counters
+    int32_t debug;  // GMR_TC_DEBUG: 1 = epilogue only drains TMEM, 2 = filter without appends (timing experiments)
 };
 
 // dynamic shared memory layout (1024-byte aligned): A' atoms (resident per user tile) | ring of B'
 // atoms (one 128 x 64 bf16 K-atom = 16 KB per stage) | bias tile | barriers | row states
-template <int NPL>
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <int NPL, bool HAS_BIAS>
+__global__ void __launch_bounds__(kTcThreads, 2)
     score_topk_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcArgs a)
 {
     constexpr int CAP = 32 * NPL;
@@ -325,7 +329,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             }
             int cnt = 0;
             float thr = -INFINITY;
-            uint64_t thr_key = 0ull;
+            // train-history mask: the item tiles are swept in ascending id order and the row's mask list is
+            // ascending too, so a cursor replaces any search; masked columns are never appended.  A row that
+            // would have fewer than KP unmasked items is left to the exact fp32 kernel (it also owns the
+            // "masked items surface once the unmasked run out" semantics of trainer.py:384).
+            int64_t mcur = mlo;
+            int mnext = (mcur < mhi) ? a.mask_items[mcur] : 0x7fffffff;
+            const bool force_exact = valid && ((int64_t)a.I - (mhi - mlo) < (int64_t)KP);
             st->cnt = 0;
             st->thr_score = -INFINITY;
             st->thr_key = 0ull;
@@ -333,7 +343,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
             for (int it = 0; it < n_itiles; ++it) {
                 const int i0 = it * kTN;
-                if (a.bias != nullptr) {
+                if (HAS_BIAS) {
                     // stage the bias tile (double-buffered with the accumulator) and sync the 4 warps
                     sm_bias[acc * kTN + et] = (i0 + et < a.I) ? a.bias[i0 + et] : 0.f;
                     asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -341,37 +351,60 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * kTN;
+                // 32 accumulator columns of this thread's row: hierarchical max (4 groups of 8) against
+                // the row threshold, scan only the groups that can contain a survivor
+                // One chunk = this thread's row x 32 accumulator columns.  The loop body is kept SMALL on
+                // purpose (not unrolled over chunks): a filter unrolled over chunks and bias variants
+                // is tens of KB of SASS and starves on instruction fetch.
 #pragma unroll 1
                 for (int c0 = 0; c0 < kTN; c0 += 32) {
                     uint32_t v[32];
                     tc_ld_32x32(taddr + c0, v);
-                    float mx = -INFINITY;
-                    if (a.bias != nullptr) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float s = __uint_as_float(v[j]) + sm_bias[acc * kTN + c0 + j];
-                            v[j] = __float_as_uint(s);
-                            mx = fmaxf(mx, s);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+                    tc_ld_wait();
+                    if (a.debug == 1) continue;
+                    const int cbase = i0 + c0;
+                    uint32_t mbits = 0u;  // masked columns of this chunk
+                    while (mnext < cbase + 32) {
+                        if (mnext >= cbase) mbits |= 1u << (mnext - cbase);
+                        ++mcur;
+                        mnext = (mcur < mhi) ? a.mask_items[mcur] : 0x7fffffff;
                     }
-                    if (valid && mx >= thr) {
+                    // hierarchical max (4 groups of 8 columns) against the row threshold: only groups that can
+                    // hold a survivor are scanned, branch-free (predicated store + counter bump)
+                    float gm[4];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            float s = __uint_as_float(v[j]);
-                            if (s >= thr) {
-                                const int item = i0 + c0 + j;
-                                if (item < a.I) {
-                                    if (mlo != mhi && sorted_contains(a.mask_items, mlo, mhi, item)) s = -1e10f;
-                                    const uint64_t key = make_key(s, item);
-                                    if (key > thr_key) my_slots[cnt++] = key;
+                    for (int g = 0; g < 4; ++g) {
+                        float m = -INFINITY;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float sj = __uint_as_float(v[g * 8 + j]);
+                            if (HAS_BIAS) {
+                                sj += sm_bias[acc * kTN + c0 + g * 8 + j];
+                                v[g * 8 + j] = __float_as_uint(sj);
+                            }
+                            m = fmaxf(m, sj);
+                        }
+                        gm[g] = m;
+                    }
+                    const float mx = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
+                    if (valid && mx >= thr && a.debug != 2) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            if (gm[g] >= thr) {
+                                const int ibase = cbase + g * 8;
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const float sj = __uint_as_float(v[g * 8 + j]);
+                                    const bool take = (sj >= thr) && (ibase + j < a.I) && !((mbits >> (g * 8 + j)) & 1u);
+                                    const uint64_t key = make_key(sj, ibase + j);
+                                    if (take) my_slots[cnt] = key;
+                                    cnt += take ? 1 : 0;
                                 }
                             }
                         }
                     }
-                    // warp-cooperative compaction of the rows that are about to run out of slots
+                    // rows about to run out of slots: cheap conservative pruning (exact compaction only when
+                    // ties defeat it)
                     unsigned need = __ballot_sync(0xffffffffu, cnt >= TRIG);
                     if (need) {
                         st->cnt = cnt;
@@ -379,11 +412,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                         while (need) {
                             const int l = __ffs(need) - 1;
                             need &= need - 1;
-                            compact_row<NPL>(cta_slots + (int64_t)(q * 32 + l) * CAP, &rows[q * 32 + l], KP - 1, lane);
+                            uint64_t* s_row = cta_slots + (int64_t)(q * 32 + l) * CAP;
+                            if (a.debug == 5 || !prune_row<NPL>(s_row, &rows[q * 32 + l], lane))
+                                compact_row<NPL>(s_row, &rows[q * 32 + l], KP - 1, lane);
                         }
                         cnt = st->cnt;
                         thr = st->thr_score;
-                        thr_key = st->thr_key;
                     }
                 }
                 tc_fence_before();
@@ -449,6 +483,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                         if (a.out_scores) a.out_scores[(int64_t)rb * a.K + j] = ok ? key_score(ek[c]) : -INFINITY;
                     }
                 }
+                if (__shfl_sync(0xffffffffu, (int)force_exact, l)) certified = false;
                 if (!certified && lane == 0) a.fallback_rows[atomicAdd(a.fallback_count, 1)] = rb;
             }
             __syncwarp();
@@ -503,7 +538,7 @@ bool score_tc_supported(int32_t D, int32_t K) { return D % 64 == 0 && D >= 64 &&
 static int tc_grid(int32_t B)
 {
     const int tiles = (B + kTM - 1) / kTM;
-    return tiles < sm_count() ? tiles : sm_count();
+    return tiles < 2 * sm_count() ? tiles : 2 * sm_count();
 }
 
 struct TcLayout {
@@ -545,7 +580,10 @@ static size_t tc_smem_fixed(int32_t D)
 }
 static int tc_stages(int32_t D)
 {
-    const int64_t room = (int64_t)227 * 1024 - (int64_t)tc_smem_fixed(D);
+    // two CTAs per SM when they fit (D = 64): 8 epilogue warps per SM hide each other's latencies and
+    // the two MMA streams share the tensor pipe; otherwise one CTA with a deep ring
+    int64_t room = (int64_t)113 * 1024 - (int64_t)tc_smem_fixed(D);
+    if (room < 3 * kTN * 128) room = (int64_t)227 * 1024 - (int64_t)tc_smem_fixed(D);
     const int s = (int)(room / (kTN * 128));
     return s > kMaxStages ? kMaxStages : s;
 }
@@ -607,13 +645,21 @@ int score_topk_tc_launch(const float* Eu, int64_t lde_u, const int64_t* users, i
     a.mask_rowptr = mask_rowptr; a.mask_items = mask_items; a.K = K; a.out_ids = out_ids; a.out_scores = out_scores;
     a.slots = (uint64_t*)(ws + L.slots); a.a_norm = a_norm; a.b_max_norm_bits = misc;
     a.fallback_rows = fallback; a.fallback_count = (int32_t*)(misc + 1); a.n_stages = n_stages;
+    a.dbg = misc;
+    a.debug = getenv("GMR_TC_DEBUG") ? atoi(getenv("GMR_TC_DEBUG")) : 0;
     const int grid = tc_grid(B);
     const int kp = tc_kp(K);
 #define GMR_TC_LAUNCH(NPL)                                                                                         \
     do {                                                                                                           \
-        GMR_CHECK_CUDA(cudaFuncSetAttribute(score_topk_tc_kernel<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                            (int)smem));                                                           \
-        score_topk_tc_kernel<NPL><<<grid, kTcThreads, smem, st>>>(map_a, map_b, a);                                \
+        if (bias != nullptr) {                                                                                     \
+            GMR_CHECK_CUDA(cudaFuncSetAttribute(score_topk_tc_kernel<NPL, true>,                                   \
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+            score_topk_tc_kernel<NPL, true><<<grid, kTcThreads, smem, st>>>(map_a, map_b, a);                      \
+        } else {                                                                                                   \
+            GMR_CHECK_CUDA(cudaFuncSetAttribute(score_topk_tc_kernel<NPL, false>,                                  \
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+            score_topk_tc_kernel<NPL, false><<<grid, kTcThreads, smem, st>>>(map_a, map_b, a);                     \
+        }                                                                                                          \
     } while (0)
     if (kp == 64)
         GMR_TC_LAUNCH(8);
@@ -629,6 +675,12 @@ int score_topk_tc_launch(const float* Eu, int64_t lde_u, const int64_t* users, i
     int rc = score_topk_simt_launch(Eu, lde_u, users, fallback, B, Ei, lde_i, bias, I, D, mask_rowptr, mask_items, K,
                                     out_ids, out_scores, ws + L.simt, st, fb_grid);
     score_simt_set_dynamic_rows(nullptr);
+    if (a.debug == 9) {
+        uint32_t h[4];
+        cudaMemcpyAsync(h, misc, sizeof(h), cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        fprintf(stderr, "[gmr tc debug] appends=%u compactions=%u fallback=%u rows=%d items=%d\n", h[2], h[3], h[1], B, I);
+    }
     return rc;
 }
 
