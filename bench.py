@@ -164,7 +164,13 @@ def run_gpu(args):
     trainer = Trainer(cfg, model)
     k = max(cfg["topk"])
     full_loader = wl.valid
-    loader = shard_loader(full_loader, rank, world)
+    sharded = None
+    if world > 1:
+        from genmmrec_b200.dist import ShardedDiffMM, shard_eval_by_user_block
+        sharded = ShardedDiffMM(model)
+        loader = shard_eval_by_user_block(full_loader, sharded.u0, sharded.u1)
+    else:
+        loader = full_loader
     n_eval_total = int(full_loader.eval_u.numel())
     host_in = HostInputs(loader, dev)
     sums_host = torch.empty((4, k), dtype=torch.float64).pin_memory()
@@ -178,8 +184,14 @@ def run_gpu(args):
 
     def hot_path(inputs):
         """propagation (uncached) -> fused score/mask/top-K -> hits + metric sums."""
-        model.invalidate_cache()
-        ids, _ = trainer.topk_all(inputs)
+        if sharded is not None:  # row-sharded propagation (fused SpMM + all-gather), user-block sharded eval
+            ue, ie = sharded.eval_factors()
+            ids, _ = ops.score_mask_topk(ue.contiguous(), ie.contiguous(), k, users=inputs.eval_u,
+                                         mask_rowptr=inputs.mask_rowptr, mask_items=inputs.mask_items,
+                                         precision=args.precision, return_scores=False)
+        else:
+            model.invalidate_cache()
+            ids, _ = trainer.topk_all(inputs)
         sums, _ = trainer.evaluator.metric_sums(ids, inputs)
         return sums
 
@@ -284,7 +296,8 @@ def run_gpu(args):
                        "n_items": wl.n_items, "nnz_train": wl.nnz_train, "eval_users": n_eval_total, "topk": k,
                        "embedding_size": cfg["embedding_size"], "n_layers": cfg["n_layers"],
                        "score_precision": args.precision,
-                       "parallelism": "user-block sharded eval x%d" % world if world > 1 else "single GPU",
+                       "parallelism": ("row-sharded propagation (push-SpMM all-gather) + user-block sharded eval, x%d" % world)
+                       if world > 1 else "single GPU",
                        "l2": ("L2 flushed between timed steps (operands fit the %d MB L2)" % (l2_bytes >> 20)) if need_flush
                        else ("operands (%.0f MB per SpMM) exceed the %d MB L2; no flush" % (operand_bytes / 1e6, l2_bytes >> 20))},
             "propagation_step_ms": prop_ms, "spmm_hbm_GBs": kernels[big_spmm]["alg_GBs"],

@@ -1,0 +1,86 @@
+"""Host-side sharding logic under a real world_size-2 process group (gloo, CPU): block bounds, the
+padded uneven all-gather, user-block sharding of the eval loader and the all-reduced metric sums."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import REPO
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, REPO)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from genmmrec_b200 import dist as gd, synth
+        from genmmrec_b200.utils.configurator import Config
+        from genmmrec_b200.utils.dataloader import EvalDataLoader
+        from genmmrec_b200.utils.dataset import RecDataset
+        from oracle import c_api
+
+        # uneven all-gather of row blocks
+        sizes = [3, 5]
+        local = torch.full((sizes[rank], 4), float(rank + 1))
+        full = gd.all_gather_rows(local, sizes)
+        assert full.shape == (8, 4) and torch.equal(full[:3], torch.ones(3, 4)) and torch.equal(full[3:], 2 * torch.ones(5, 4))
+
+        # nnz-balanced bounds cover everything, monotone, balanced within one row
+        deg = torch.tensor(np.random.default_rng(0).zipf(1.5, size=1000).clip(max=500))
+        rowptr = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(deg, 0)])
+        b = gd.nnz_balanced_bounds(rowptr, world)
+        assert b[0] == 0 and b[-1] == 1000 and all(b[i] <= b[i + 1] for i in range(world))
+        per = [int(rowptr[b[g + 1]] - rowptr[b[g]]) for g in range(world)]
+        assert abs(per[0] - per[1]) <= 2 * int(deg.max())
+        assert gd.block_bounds(10, 3) == [0, 3, 6, 10]
+
+        # user-block sharded evaluation == unsharded evaluation (metric SUMS are additive)
+        cfg = Config("LightGCN", "toy", {"device": "cpu", "is_multimodal_model": False})
+        u, i, lab = synth.make_interactions(300, 120, 3600)
+        tr, va, _ = RecDataset.from_arrays(cfg, u, i, lab, 300, 120).split()
+        loader = EvalDataLoader(cfg, va, additional_dataset=tr, batch_size=64)
+        ub = gd.block_bounds(300, world)
+        sh = gd.shard_eval_by_user_block(loader, ub[rank], ub[rank + 1])
+        n_local = torch.tensor([sh.eval_u.numel()])
+        dist.all_reduce(n_local)
+        assert int(n_local) == loader.eval_u.numel()
+        pos = sh.positions.numpy()
+        assert np.array_equal(sh.eval_u.numpy() + ub[rank], loader.eval_u.numpy()[pos])
+        rp, it = loader.mask_rowptr.numpy(), loader.mask_items.numpy()
+        srp, sit = sh.mask_rowptr.numpy(), sh.mask_items.numpy()
+        for j in (0, len(pos) // 2, len(pos) - 1):
+            assert np.array_equal(sit[srp[j]:srp[j + 1]], it[rp[pos[j]]:rp[pos[j] + 1]])
+        # fake top-K ids; per-rank oracle metric sums all-reduce to the global sums
+        rng = np.random.default_rng(1)
+        topk = np.stack([rng.choice(120, size=20, replace=False) for _ in range(loader.eval_u.numel())]).astype(np.int32)
+        hit_all = c_api.hits(topk, loader.gt_rowptr.numpy(), loader.gt_items.numpy())
+        m_all = c_api.metrics(hit_all, loader.eval_len_list)
+        hit_loc = c_api.hits(topk[pos], sh.gt_rowptr.numpy(), sh.gt_items.numpy())
+        m_loc = c_api.metrics(hit_loc, sh.eval_len_list)
+        sums = torch.tensor(np.stack([m_loc[k] for k in ("recall", "ndcg", "precision", "map")]) * len(pos))
+        dist.all_reduce(sums)
+        want = np.stack([m_all[k] for k in ("recall", "ndcg", "precision", "map")])
+        assert np.abs(sums.numpy() / loader.eval_u.numel() - want).max() < 1e-12
+        out.put((rank, "ok"))
+    except Exception as e:  # surface the failure in the parent
+        import traceback
+        out.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharding_logic_world2():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [out.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in results:
+        assert msg == "ok", "rank %d failed:\n%s" % (rank, msg)
