@@ -415,7 +415,17 @@ def run_reference(args):
     }
 
 
+def _claim_stdout():
+    """Route everything libraries print on fd 1 (e.g. NCCL's version banner) to stderr and return a
+    writer on the real stdout, so that the ONE JSON line is the only thing the driver reads there."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
 def main():
+    out_stream = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -434,7 +444,8 @@ def main():
     if args.impl == "reference":
         out = run_reference(args)
         if out is not None:
-            print(json.dumps(out))
+            out_stream.write(json.dumps(out) + "\n")
+            out_stream.flush()
         return
 
     out, wl, trainer, loader = run_gpu(args)
@@ -457,7 +468,8 @@ def main():
             if not args.no_cpu_baseline:
                 extra["cpu_baseline"], _ = cpu_baseline(wl2, ld2, steps=1, warmup=1)
             out["workloads"] = {WORKLOAD_NAMES["baby"]: extra}
-        print(json.dumps(out))
+        out_stream.write(json.dumps(out) + "\n")
+        out_stream.flush()
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
