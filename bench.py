@@ -279,7 +279,8 @@ def run_gpu(args):
                 "frac": kernels[score_key]["alg_TFLOPs"] / tensor_peak, "traffic": None,
                 "peak_source": peaks["source"] + " bf16 sustained (kernel timed inside a long step)",
                 "share_of_step": score_share,
-                "note": "algorithmic flops 2*U*I*D (the tc mode issues 3x that many bf16 flops for the split-precision "
+                "note": "algorithmic flops 2*U*I*D of the reference's dense matmul (the tc mode sweeps items in descending-norm order "
+                        "and stops when no remaining item can reach any top-K list, so it may execute far fewer; tc_split issues 3x "
                         "product; fp32 mode runs the exact fmaf chain on CUDA cores)"}
     roofline_spmm = {"kernel": big_spmm, "bound": "hbm", "achieved": kernels[big_spmm]["alg_GBs"],
                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": kernels[big_spmm]["alg_GBs"] / peaks["hbm_gbs"],

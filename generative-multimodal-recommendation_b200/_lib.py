@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "libgmr.so")
 
 GMR_SCORE_FP32 = 0
 GMR_SCORE_TC = 1
+GMR_SCORE_TC_SPLIT = 2
 GMR_MAX_TOPK = 256
 GMR_PEER_HANDLE_BYTES = 64
 
@@ -32,7 +33,8 @@ SIGNATURES = {
     "gmr_score_topk_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32, _i32]),
     "gmr_score_mask_topk_f32": (C.c_int, [_vp, _i64, _vp, _i32, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _i32, _i32, _vp,
                                           _vp, _vp, _i64, _vp]),
-    "gmr_score_tc_fallback_rows": (C.c_int, [_vp, _i32, _i32, _i32, _i32, C.POINTER(_i32), _vp]),
+    "gmr_score_tc_fallback_rows": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, C.POINTER(_i32), _vp]),
+    "gmr_score_tc_stats": (C.c_int, [_vp, _i32, _i32, _i32, _i32, C.POINTER(C.c_uint64), _vp]),
     "gmr_scores_f32": (C.c_int, [_vp, _i64, _vp, _i32, _vp, _i64, _vp, _i32, _i32, _vp, _i64, _vp]),
     "gmr_hits_metrics_workspace_bytes": (_i64, [_i32, _i32]),
     "gmr_hits_metrics": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),

@@ -47,6 +47,17 @@ int score_topk_tc_launch(const float* Eu, int64_t lde_u, const int64_t* users, i
 
 int score_tc_fallback_count(const void* workspace, int32_t B, int32_t I, int32_t D, int32_t K, int32_t* count_host,
                             cudaStream_t st);
+// score_topk_screen.cu
+bool score_screen_supported(int32_t D, int32_t K);
+int64_t score_screen_workspace_bytes(int32_t B, int32_t I, int32_t D, int32_t K);
+int score_topk_screen_launch(const float* Eu, int64_t lde_u, const int64_t* users, int32_t B, const float* Ei,
+                             int64_t lde_i, const float* bias, int32_t I, int32_t D, const int64_t* mask_rowptr,
+                             const int32_t* mask_items, int32_t K, int32_t* out_ids, float* out_scores, void* workspace,
+                             int64_t workspace_bytes, cudaStream_t st);
+int score_screen_fallback_count(const void* workspace, int32_t B, int32_t I, int32_t D, int32_t K, int32_t* count_host,
+                                cudaStream_t st);
+int score_screen_stats(const void* workspace, int32_t B, int32_t I, int32_t D, int32_t K, uint64_t* stats_host,
+                       cudaStream_t st);
 
 }  // namespace gmr
 
@@ -82,7 +93,8 @@ extern "C" int64_t gmr_score_topk_workspace_bytes(int32_t B, int32_t I, int32_t 
 {
     if (B <= 0 || I <= 0 || D <= 0 || K <= 0 || K > GMR_MAX_TOPK) return 0;
     int64_t simt = gmr::score_simt_workspace_bytes(B, K);
-    if (precision == GMR_SCORE_TC && gmr::score_tc_supported(D, K)) return gmr::score_tc_workspace_bytes(B, I, D, K);
+    if (precision == GMR_SCORE_TC && gmr::score_screen_supported(D, K)) return gmr::score_screen_workspace_bytes(B, I, D, K);
+    if (precision == GMR_SCORE_TC_SPLIT && gmr::score_tc_supported(D, K)) return gmr::score_tc_workspace_bytes(B, I, D, K);
     return gmr::align_up(simt, 256);
 }
 
@@ -94,8 +106,8 @@ extern "C" int gmr_score_mask_topk_f32(const float* Eu, int64_t lde_u, const int
 {
     GMR_REQUIRE(B >= 0 && I >= 1 && D >= 1, "gmr_score_mask_topk_f32: bad shape B=%d I=%d D=%d", B, I, D);
     GMR_REQUIRE(K >= 1 && K <= GMR_MAX_TOPK, "gmr_score_mask_topk_f32: K=%d outside [1, %d]", K, GMR_MAX_TOPK);
-    GMR_REQUIRE(precision == GMR_SCORE_FP32 || precision == GMR_SCORE_TC, "gmr_score_mask_topk_f32: unknown precision %d",
-                precision);
+    GMR_REQUIRE(precision == GMR_SCORE_FP32 || precision == GMR_SCORE_TC || precision == GMR_SCORE_TC_SPLIT,
+                "gmr_score_mask_topk_f32: unknown precision %d", precision);
     if (B == 0) return GMR_OK;
     GMR_REQUIRE(Eu && Ei && out_ids, "gmr_score_mask_topk_f32: null operand");
     GMR_REQUIRE(lde_u >= D && lde_i >= D, "gmr_score_mask_topk_f32: leading dimension smaller than D");
@@ -108,8 +120,16 @@ extern "C" int gmr_score_mask_topk_f32(const float* Eu, int64_t lde_u, const int
     }
     cudaStream_t st = (cudaStream_t)stream;
     if (precision == GMR_SCORE_TC) {
+        if (!gmr::score_screen_supported(D, K)) {
+            gmr::set_error("gmr_score_mask_topk_f32: GMR_SCORE_TC needs D %% 64 == 0, D <= 256 and K <= 256 (got D=%d, K=%d)", D, K);
+            return GMR_ERR_UNSUPPORTED;
+        }
+        return gmr::score_topk_screen_launch(Eu, lde_u, users, B, Ei, lde_i, bias, I, D, mask_rowptr, mask_items, K,
+                                             out_ids, out_scores, workspace, workspace_bytes, st);
+    }
+    if (precision == GMR_SCORE_TC_SPLIT) {
         if (!gmr::score_tc_supported(D, K)) {
-            gmr::set_error("gmr_score_mask_topk_f32: GMR_SCORE_TC needs D %% 64 == 0, D <= 256 and K <= 248 (got D=%d, K=%d)", D, K);
+            gmr::set_error("gmr_score_mask_topk_f32: GMR_SCORE_TC_SPLIT needs D %% 64 == 0, D <= 192 and K <= 248 (got D=%d, K=%d)", D, K);
             return GMR_ERR_UNSUPPORTED;
         }
         return gmr::score_topk_tc_launch(Eu, lde_u, users, B, Ei, lde_i, bias, I, D, mask_rowptr, mask_items, K,
@@ -120,14 +140,24 @@ extern "C" int gmr_score_mask_topk_f32(const float* Eu, int64_t lde_u, const int
 }
 
 extern "C" int gmr_score_tc_fallback_rows(const void* workspace, int32_t B, int32_t I, int32_t D, int32_t K,
-                                          int32_t* count_host, void* stream)
+                                          int32_t precision, int32_t* count_host, void* stream)
 {
     GMR_REQUIRE(workspace && count_host, "gmr_score_tc_fallback_rows: null argument");
-    if (!gmr::score_tc_supported(D, K)) {
-        *count_host = 0;
-        return GMR_OK;
-    }
-    return gmr::score_tc_fallback_count(workspace, B, I, D, K, count_host, (cudaStream_t)stream);
+    *count_host = 0;
+    if (precision == GMR_SCORE_TC && gmr::score_screen_supported(D, K))
+        return gmr::score_screen_fallback_count(workspace, B, I, D, K, count_host, (cudaStream_t)stream);
+    if (precision == GMR_SCORE_TC_SPLIT && gmr::score_tc_supported(D, K))
+        return gmr::score_tc_fallback_count(workspace, B, I, D, K, count_host, (cudaStream_t)stream);
+    return GMR_OK;
+}
+
+extern "C" int gmr_score_tc_stats(const void* workspace, int32_t B, int32_t I, int32_t D, int32_t K,
+                                  uint64_t* stats_host, void* stream)
+{
+    GMR_REQUIRE(workspace && stats_host, "gmr_score_tc_stats: null argument");
+    for (int i = 0; i < 8; ++i) stats_host[i] = 0;
+    if (!gmr::score_screen_supported(D, K)) return GMR_OK;
+    return gmr::score_screen_stats(workspace, B, I, D, K, stats_host, (cudaStream_t)stream);
 }
 
 extern "C" int gmr_scores_f32(const float* Eu, int64_t lde_u, const int64_t* users, int32_t B, const float* Ei,

@@ -1,0 +1,958 @@
+// score_topk_screen.cu -- K2 + K3, second generation: fused score + mask + top-K where the dense
+// contraction is ONE fp16 tcgen05 pass used as a certified SCREEN over a NORM-ORDERED catalogue, followed by
+// an exact fp32 re-score of the few candidates that can still reach the top K.  sm_100a only.
+//
+// Replaces the same reference call chain as score_topk_simt.cu / score_topk_tc.cu
+//   torch.matmul(u_e[user], i_e.T) -> scores[mask] = -1e10 -> torch.topk   (models/diffmm.py:276-278,
+//   common/trainer.py:381-386) and returns THE SAME ids/scores as the fp32 path.
+//
+//   1. operands: user rows are scaled by a per-row power of two, item rows by one global power of two
+//      (exact, order-preserving per row) so that every element fits fp16 with 11 significant bits, then
+//      rounded to fp16.  The approximate score s~ (fp32 accumulation in TMEM) obeys
+//          |s~(u, i) - s(u, i)| <= eps(u, i) = kScreenErr * |u|_2 * |e_i|_2 + small absolute term   (scaled units)
+//      (2 * 2^-11 operand rounding + accumulation slack; subnormal flushes are covered by the absolute term).
+//      The bound is PER ITEM: propagated item embeddings have a heavy-tailed norm distribution (max/median
+//      ~ 85 at the 1M-user shape), a max-norm bound would keep hundreds of useless candidates per row.
+//   2. screen: every item has an interval [lb, ub] = s~ -+ eps around its exact score.  If L is the K-th
+//      largest lb among ANY set of unmasked items of the row, the exact K-th best score is >= L, so an item
+//      with ub < L cannot be among the exact top K.  The sweep keeps, per row, every item with ub >= the
+//      running L; nothing else is ever stored.  Whole 32-column chunks are rejected with one compare.
+//   3. norm order + early stop (exact maximum-inner-product pruning by Cauchy-Schwarz): items are swept in
+//      DESCENDING NORM order (cub radix sort per call), so every item at or after sweep position p
+//      scores at most |u| * nb[p].  Once |u| * nb[p] < L for all 256 rows of a CTA, no remaining item
+//      can enter any of their top-K lists and the CTA stops sweeping.  With popularity-skewed
+//      embeddings this ends after a few tiles; with flat norms it degenerates to the full sweep.  The
+//      stop tile is agreed by all warps at doubling checkpoints (1, 2, 4, ... tiles), so a full sweep pays
+//      ~12 pipeline drains.
+//   4. one persistent CTA per SM owns 2 x 128 users: each TMA-loaded item tile (128 items) is
+//      multiplied against BOTH resident user tiles (the item operand is read from L2 once per 256
+//      users), accumulators double-buffered in all 512 TMEM columns:
+//        warp 0      TMA producer
+//        warp 1      MMA issuer (one elected thread)
+//        warps 2-9   epilogue: thread = user row.  Fast path per 32 columns: tcgen05.ld, a 3-input max
+//                    tree, one compare against the row threshold.  Rows that see a survivor dump the 32
+//                    scores to a swizzled shared-memory strip and the WARP appends them cooperatively
+//                    (lane = column), so a hit costs the warp ~12 instructions instead of a 32-way
+//                    divergent scan.  The train-history mask is applied when a row's buffer is pruned
+//                    (256 binary searches in flight), never per score.
+//   5. end of a user tile: prune, exact fp32 fmaf re-score of the survivors, sort by (score desc, id asc),
+//      write the top K.  Rows whose buffer overflowed (massive near-ties), rows with fewer than K
+//      unmasked items and rows with non-finite scores are queued for the fp32 kernel.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <cstdlib>
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include "topk_select.cuh"
+
+namespace gmr {
+
+// fp32 kernel entry used for the queued rows (score_topk_simt.cu)
+int score_topk_simt_launch(const float* Eu, int64_t lde_u, const int64_t* users, const int32_t* row_map,
+                           int32_t n_rows, const float* Ei, int64_t lde_i, const float* bias, int32_t I, int32_t D,
+                           const int64_t* mask_rowptr, const int32_t* mask_items, int32_t K, int32_t* out_ids,
+                           float* out_scores, void* workspace, cudaStream_t st, int grid_override);
+int64_t score_simt_workspace_bytes(int32_t B, int32_t K);
+void score_simt_set_dynamic_rows(const int32_t* n_rows_dev);
+
+constexpr int kSM = 128;                        // users per UMMA tile (M)
+constexpr int kSN = 128;                        // items per tile (N)
+constexpr int kUT = 2;                          // user tiles per CTA
+constexpr int kRowsPerCta = kUT * kSM;          // 256
+constexpr int kEpiWarps = kUT * 4;              // 8
+constexpr int kScrThreads = 64 + kEpiWarps * 32;  // 320
+constexpr int kScrMaxStages = 10;
+constexpr uint32_t kAtomBytes = 128 * 128;      // one 128-row x 64-half K-atom
+constexpr float kScreenErr = 1.05e-3f;          // 2^-10 (1 + 2^-11) operand rounding + accumulation slack
+constexpr int kStatSlots = 8;
+
+// ---- 1. operand preparation ---------------------------------------------------------------------
+__device__ __forceinline__ float pow2_scale_for(float absmax)
+{
+    // power of two s with absmax * s in [2^13, 2^14); 1 for zero / non-finite input
+    if (!(absmax > 0.f) || !(absmax < INFINITY)) return 1.f;
+    const int e = (int)((__float_as_uint(absmax) >> 23) & 0xffu) - 127;
+    int sh = 13 - e;
+    sh = sh < -60 ? -60 : (sh > 60 ? 60 : sh);
+    return __uint_as_float((uint32_t)(sh + 127) << 23);
+}
+
+__global__ void __launch_bounds__(256)
+    absmax_kernel(const float* __restrict__ E, int64_t lde, int64_t n_rows, int32_t D, uint32_t* __restrict__ out_bits)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t w0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+    float m = 0.f;
+    for (int64_t r = w0; r < n_rows; r += nw)
+        for (int d = lane; d < D; d += 32) m = fmaxf(m, fabsf(E[r * lde + d]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0 && m > 0.f) atomicMax(out_bits, __float_as_uint(m));
+}
+
+// item norms in scaled units (rounded up: they feed BOUNDS) as sortable bits + the identity permutation
+__global__ void __launch_bounds__(256)
+    item_norms_kernel(const float* __restrict__ E, int64_t lde, int32_t n_rows, int32_t D,
+                      const uint32_t* __restrict__ gmax_bits, uint32_t* __restrict__ norm_bits, int32_t* __restrict__ ident)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n_rows) return;
+    const float s = pow2_scale_for(__uint_as_float(*gmax_bits));
+    float ss = 0.f;
+    for (int d = lane; d < D; d += 32) {
+        const float x = E[r * lde + d] * s;
+        ss = fmaf(x, x, ss);
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, m);
+    if (lane == 0) {
+        float nrm = sqrtf(ss) * 1.000001f;
+        if (!(nrm < INFINITY)) nrm = 3.0e38f;  // NaN / inf rows sort first and never allow an early stop
+        norm_bits[r] = __float_as_uint(nrm);
+        ident[r] = (int32_t)r;
+    }
+}
+
+// items in sweep order: out[p, :] = fp16(E[perm[p], :] * s_i); positions >= n_rows are zero rows with
+// norm 0 and id -1
+__global__ void __launch_bounds__(256)
+    prep_items_kernel(const float* __restrict__ E, int64_t lde, int32_t n_rows, int32_t n_rows_pad, int32_t D,
+                      const uint32_t* __restrict__ gmax_bits, int32_t* __restrict__ perm, float* __restrict__ nb,
+                      __half* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= n_rows_pad) return;
+    const float s = pow2_scale_for(__uint_as_float(*gmax_bits));
+    __half* o = out + p * (int64_t)D;
+    const float* src = (p < n_rows) ? E + (int64_t)perm[p] * lde : nullptr;
+    for (int d = lane; d < D; d += 32) o[d] = __float2half_rn(src ? src[d] * s : 0.f);
+    if (lane == 0 && p >= n_rows) {
+        perm[p] = -1;
+        nb[p] = 0.f;
+    }
+}
+
+// users: per-row power-of-two scale; writes the row's error coefficients (eps(u, i) = ce * |e_i| + ab, scaled
+// units), its norm and the bias scale
+struct RowConst {
+    float ce, ab;   // eps(u, i) = ce * nb[i] + ab
+    float na;       // scaled row norm (rounded up)
+    float sc;       // s_u * s_i: scale applied to the bias
+};
+
+__global__ void __launch_bounds__(256)
+    prep_users_kernel(const float* __restrict__ E, int64_t lde, const int64_t* __restrict__ rows, int32_t n_rows,
+                      int32_t n_rows_pad, int32_t D, const uint32_t* __restrict__ gmax_bits, const float* __restrict__ nb,
+                      const uint32_t* __restrict__ biasmax_bits, __half* __restrict__ out, RowConst* __restrict__ row_const)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n_rows_pad) return;
+    __half* o = out + r * (int64_t)D;
+    const float* src = (r < n_rows) ? E + (rows ? rows[r] : r) * lde : nullptr;
+    float m = 0.f;
+    if (src)
+        for (int d = lane; d < D; d += 32) m = fmaxf(m, fabsf(src[d]));
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, k));
+    const float su = pow2_scale_for(m);
+    float ss = 0.f;
+    for (int d = lane; d < D; d += 32) {
+        const float x = src ? src[d] * su : 0.f;
+        o[d] = __float2half_rn(x);
+        ss = fmaf(x, x, ss);
+    }
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, k);
+    if (lane == 0) {
+        float na = sqrtf(ss) * 1.000001f;
+        if (!(na < INFINITY)) na = INFINITY;
+        const float nbmax = nb[0];  // sweep order is norm-descending
+        const float si = pow2_scale_for(__uint_as_float(*gmax_bits));
+        RowConst rc;
+        rc.sc = su * si;
+        rc.ce = kScreenErr * na;
+        rc.ab = 1e-6f * (na + nbmax);
+        if (biasmax_bits != nullptr) {
+            rc.ce += 2.4e-7f * na;
+            rc.ab += 2.4e-7f * rc.sc * __uint_as_float(*biasmax_bits);
+        }
+        rc.na = na;
+        row_const[r] = rc;
+    }
+}
+
+// ---- 2. selection helpers (warp-cooperative, one row at a time) -----------------------------------
+struct PruneResult {
+    int cnt;      // keys kept in slots [0, cnt); -1: the row overflowed (near-ties defeat the screen)
+    float lbK;    // new lower bound L of the row's exact K-th best score (approximate-score units)
+};
+
+// Keep only the keys that can still matter.  Keys at positions >= n_checked are first tested against the
+// row's train-history list (ascending item ids, binary search) and dropped when masked.  Every remaining
+// key (s~, sweep position p) carries the interval [lb, ub] = s~ -+ (ce * nb[p] + ab).  L = K-th
+// largest lb of a POOL of keys (any subset of the row's unmasked keys gives a valid lower bound of the
+// exact K-th score): the pool is each lane's M = NPL / 2 largest lb (32 * M >= 2 K keys; with slots
+// filled in arrival order the pool's K-th is within a few ranks of the true K-th), sorted with a 32-bit
+// bitonic network.  Keys with ub < L are dropped, the rest compacted in place (unsorted).  If that frees
+// too little, L is recomputed from ALL keys (exact K-th lb).
+//
+// Key layout here: (ordered s~) << 32 | sweep position p  (NOT the item id: nb[] and perm[] are indexed by p).
+template <int NPL>
+__device__ __noinline__ PruneResult screen_prune(uint64_t* __restrict__ s_row, int cnt, int n_checked, float ce, float ab,
+                                                 const float* __restrict__ nb, const int32_t* __restrict__ perm,
+                                                 const int32_t* __restrict__ mask_items, int64_t mlo, int64_t mhi, int K,
+                                                 int lane, unsigned long long* stats)
+{
+    constexpr int CAP = 32 * NPL;
+    constexpr int M = NPL / 2;
+    uint64_t k[NPL];
+    uint32_t lb[NPL];  // order-preserving bits; 0 = empty
+    float ub[NPL];
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) {
+        const int i = r * 32 + lane;
+        k[r] = (i < cnt) ? s_row[i] : 0ull;
+    }
+    if (mlo < mhi) {
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) {
+            const int i = r * 32 + lane;
+            if (k[r] != 0ull && i >= n_checked && sorted_contains(mask_items, mlo, mhi, perm[(uint32_t)k[r]])) k[r] = 0ull;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) {
+        lb[r] = 0u;
+        ub[r] = -INFINITY;
+        if (k[r] != 0ull) {
+            const float e = fmaf(ce, nb[(uint32_t)k[r]], ab);
+            const float sc = ordered_to_f32((uint32_t)(k[r] >> 32));
+            lb[r] = f32_to_ordered(sc - e);
+            ub[r] = sc + e;
+        }
+    }
+    // pool: per-lane M largest lb (insertion into a tiny sorted list)
+    uint32_t pool[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) pool[m] = 0u;
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) {
+        uint32_t x = lb[r];
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            const uint32_t hi = pool[m] > x ? pool[m] : x;
+            x = pool[m] > x ? x : pool[m];
+            pool[m] = hi;
+        }
+    }
+    warp_bitonic_sort_desc<M, uint32_t>(pool, lane);
+    const int kth = K - 1;  // K <= 32 * M
+    uint32_t lk = 0u;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        const uint32_t cand = __shfl_sync(0xffffffffu, pool[m], kth & 31);
+        if (m == (kth >> 5)) lk = cand;
+    }
+    float L = (lk != 0u) ? ordered_to_f32(lk) : -INFINITY;
+    int total = 0;
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) total += __popc(__ballot_sync(0xffffffffu, lb[r] != 0u && ub[r] >= L));
+    bool exact = false;
+    if (total > CAP * 5 / 8) {
+        // exact K-th largest lb over all keys
+        exact = true;
+        uint32_t all[NPL];
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) all[r] = lb[r];
+        warp_bitonic_sort_desc<NPL, uint32_t>(all, lane);
+        lk = 0u;
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) {
+            const uint32_t cand = __shfl_sync(0xffffffffu, all[r], kth & 31);
+            if (r == (kth >> 5)) lk = cand;
+        }
+        L = (lk != 0u) ? ordered_to_f32(lk) : -INFINITY;
+        total = 0;
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) total += __popc(__ballot_sync(0xffffffffu, lb[r] != 0u && ub[r] >= L));
+    }
+    // compact survivors in place (order is irrelevant)
+    int mine = 0;
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) mine += (lb[r] != 0u && ub[r] >= L) ? 1 : 0;
+    int pre = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, pre, o);
+        if (lane >= o) pre += y;
+    }
+    int pos = pre - mine;
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < NPL; ++r)
+        if (lb[r] != 0u && ub[r] >= L) s_row[pos++] = k[r];
+    __syncwarp();
+    if (stats && lane == 0) atomicAdd(&stats[exact ? 3 : 2], 1ull);
+    PruneResult res;
+    res.cnt = (total > CAP - 64) ? -1 : total;
+    res.lbK = (total > CAP - 64) ? INFINITY : L;
+    return res;
+}
+
+// ---- 3. the fused kernel ----------------------------------------------------------------------------
+struct ScrArgs {
+    const float* Eu;
+    int64_t lde_u;
+    const int64_t* users;
+    int32_t B;
+    const float* Ei;
+    int64_t lde_i;
+    const float* bias;
+    int32_t I, D;
+    const int64_t* mask_rowptr;
+    const int32_t* mask_items;
+    int32_t K;
+    int32_t* out_ids;
+    float* out_scores;
+    uint64_t* slots;            // [grid][kRowsPerCta][CAP]
+    const RowConst* row_const;  // [B_pad]
+    const float* nb;            // [I_pad] scaled item norms in sweep order (descending, rounded up)
+    const int32_t* perm;        // [I_pad] sweep position -> item id (-1: padding)
+    const uint32_t* biasmax_bits;
+    int32_t* fallback_rows;     // [B]
+    int32_t* fallback_count;    // [1]
+    int32_t n_stages;
+    int32_t vec4;               // Eu / Ei rows are 16-byte aligned
+    int32_t first_check;        // tiles before the first stop check
+    unsigned long long* stats;  // [kStatSlots] or null
+    int32_t debug;              // GMR_TC_DEBUG timing experiments: 1 = drain TMEM only, 2 = filter without appends,
+                                // 3 = no early stop (full sweep; results stay exact)
+};
+
+template <int NSORT>
+__device__ __forceinline__ void final_sort_write(uint64_t (&ek)[NSORT], int lane, const ScrArgs& a, int64_t rb)
+{
+    warp_bitonic_sort_desc<NSORT>(ek, lane);
+#pragma unroll
+    for (int c = 0; c < NSORT; ++c) {
+        const int j = c * 32 + lane;
+        if (j < a.K) {
+            const bool ok = ek[c] != 0ull;
+            a.out_ids[rb * a.K + j] = ok ? key_id(ek[c]) : -1;
+            if (a.out_scores) a.out_scores[rb * a.K + j] = ok ? key_score(ek[c]) : -INFINITY;
+        }
+    }
+}
+
+// exact fp32 score of the item at sweep position p (same fmaf chain as the fp32 kernel and the oracle)
+__device__ __forceinline__ uint64_t exact_key(const ScrArgs& a, const float* __restrict__ u, uint32_t p)
+{
+    const int item = a.perm[p];
+    const float* e = a.Ei + (int64_t)item * a.lde_i;
+    float s = a.bias ? a.bias[item] : 0.f;
+    if (a.vec4) {
+        const float4* e4 = reinterpret_cast<const float4*>(e);
+        const float4* u4 = reinterpret_cast<const float4*>(u);
+        for (int d = 0; d < a.D / 4; ++d) {
+            const float4 ev = __ldg(e4 + d);
+            const float4 uv = __ldg(u4 + d);
+            s = fmaf(uv.x, ev.x, s);
+            s = fmaf(uv.y, ev.y, s);
+            s = fmaf(uv.z, ev.z, s);
+            s = fmaf(uv.w, ev.w, s);
+        }
+    } else {
+        for (int d = 0; d < a.D; ++d) s = fmaf(u[d], e[d], s);
+    }
+    return make_key(s, item);
+}
+
+template <int NSORT>
+__device__ __forceinline__ void rescore_sort_write(const ScrArgs& a, const float* __restrict__ urow,
+                                                   const uint64_t* __restrict__ s_row, int cnt, int lane, int64_t rb)
+{
+    uint64_t ek[NSORT];
+#pragma unroll
+    for (int c = 0; c < NSORT; ++c) {
+        const int j = c * 32 + lane;
+        ek[c] = (j < cnt) ? exact_key(a, urow, (uint32_t)s_row[j]) : 0ull;
+    }
+    final_sort_write<NSORT>(ek, lane, a, rb);
+}
+
+template <int NPL, bool HAS_BIAS>
+__global__ void __launch_bounds__(kScrThreads, 1)
+    score_screen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, ScrArgs a)
+{
+    constexpr int CAP = 32 * NPL;
+    constexpr int TRIG = CAP - 32;
+
+    extern __shared__ uint8_t smem_dyn[];
+    uint8_t* smem_raw = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    const int n_atoms = a.D / 64;
+    const int n_stages = a.n_stages;
+    uint8_t* sm_a = smem_raw;                                         // [kUT][n_atoms][16 KB]
+    uint8_t* sm_b = sm_a + (size_t)kUT * n_atoms * kAtomBytes;        // [n_stages][16 KB]
+    float* sm_strip = reinterpret_cast<float*>(sm_b + (size_t)n_stages * kAtomBytes);  // [kEpiWarps][32][32]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm_strip + kEpiWarps * 1024);
+    uint64_t* full_b = bars;                                  // [kScrMaxStages]
+    uint64_t* empty_b = bars + kScrMaxStages;                 // [kScrMaxStages]
+    uint64_t* tmem_full = bars + 2 * kScrMaxStages;           // [kUT][2]
+    uint64_t* tmem_empty = bars + 2 * kScrMaxStages + 4;      // [kUT][2]
+    uint64_t* a_full = bars + 2 * kScrMaxStages + 8;
+    uint64_t* a_empty = bars + 2 * kScrMaxStages + 9;
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kScrMaxStages + 10);
+    int* sm_need = reinterpret_cast<int*>(bars + 2 * kScrMaxStages + 11);  // tiles still needed by this CTA's rows
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_groups = (a.B + kRowsPerCta - 1) / kRowsPerCta;
+    const int n_itiles = (a.I + kSN - 1) / kSN;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < n_stages; ++s) {
+            mbar_init(&full_b[s], 1);
+            mbar_init(&empty_b[s], 1);
+        }
+        for (int s = 0; s < 2 * kUT; ++s) {
+            mbar_init(&tmem_full[s], 1);
+            mbar_init(&tmem_empty[s], 128);
+        }
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
+        *sm_need = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
+                     "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    // per-role persistent state (counters run across segments and user groups)
+    uint32_t g = 0, t = 0, a_phase = 0;            // B'-atom counter, item-tile counter, A' barrier phase
+    const int ew = warp - 2;
+    const int u = (ew >> 2) & 1;
+    const int q = warp & 3;
+    const int row_cta = u * kSM + q * 32 + lane;  // epilogue: row inside the CTA's 256 users
+    const int warp_row0 = u * kSM + q * 32;
+    uint64_t* cta_slots = a.slots + (int64_t)blockIdx.x * kRowsPerCta * CAP;
+    float* strip = sm_strip + (ew < 0 ? 0 : ew) * 1024;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const float bias_abs_max = (HAS_BIAS && a.biasmax_bits) ? __uint_as_float(*a.biasmax_bits) : 0.f;
+    unsigned long long st_slow = 0, st_app = 0, st_resc = 0, st_tiles = 0;
+
+    for (int ug = blockIdx.x; ug < n_groups; ug += gridDim.x) {
+        // ---- group prologue ----
+        int cnt = 0, chk = 0;
+        float L = INFINITY;
+        RowConst rc = {0.f, 0.f, 0.f, 0.f};
+        int64_t mlo = 0, mhi = 0;
+        bool force_exact = false;
+        if (warp == 0) {
+            if (lane == 0) {
+                mbar_wait(a_empty, a_phase ^ 1);
+                mbar_expect_tx(a_full, (uint32_t)(kUT * n_atoms) * kAtomBytes);
+                for (int uu = 0; uu < kUT; ++uu)
+                    for (int k = 0; k < n_atoms; ++k)
+                        tma_load_2d(sm_a + (size_t)(uu * n_atoms + k) * kAtomBytes, &map_a, a_full, k * 64,
+                                    (ug * kUT + uu) * kSM);
+                a_phase ^= 1;
+            }
+        } else if (warp == 1) {
+            if (lane == 0) {
+                mbar_wait(a_full, a_phase);
+                a_phase ^= 1;
+            }
+        } else {
+            const int64_t b = (int64_t)ug * kRowsPerCta + row_cta;
+            if (b < a.B) {
+                rc = a.row_const[b];
+                L = -INFINITY;  // running lower bound of the row's exact K-th score
+                if (a.mask_rowptr != nullptr) {
+                    mlo = a.mask_rowptr[b];
+                    mhi = a.mask_rowptr[b + 1];
+                }
+                force_exact = (int64_t)a.I - (mhi - mlo) < (int64_t)a.K;
+                if (force_exact || !(rc.na < INFINITY)) L = INFINITY;  // redone on the fp32 path: nothing to collect
+            }
+        }
+
+        // ---- sweep in segments [it, seg_end); the stop tile is re-agreed at doubling checkpoints ----
+        int it = 0, it_end = n_itiles, next_check = a.first_check;
+        while (it < it_end) {
+            const int seg_end = it_end < next_check ? it_end : next_check;
+            if (warp == 0) {
+                // ===== TMA producer =====
+                if (lane == 0) {
+                    for (int i2 = it; i2 < seg_end; ++i2) {
+                        for (int k = 0; k < n_atoms; ++k, ++g) {
+                            const uint32_t stage = g % (uint32_t)n_stages, ph = (g / (uint32_t)n_stages) & 1u;
+                            mbar_wait(&empty_b[stage], ph ^ 1);
+                            mbar_expect_tx(&full_b[stage], kAtomBytes);
+                            tma_load_2d(sm_b + (size_t)stage * kAtomBytes, &map_b, &full_b[stage], k * 64, i2 * kSN);
+                        }
+                    }
+                }
+            } else if (warp == 1) {
+                // ===== MMA issuer (one elected thread) =====
+                if (lane == 0) {
+                    const uint32_t idesc = umma_idesc_f16(kSM, kSN);
+                    for (int i2 = it; i2 < seg_end; ++i2, ++t) {
+                        const uint32_t acc = t & 1u, acc_phase = (t >> 1) & 1u;
+                        for (int k = 0; k < n_atoms; ++k) {
+                            const uint32_t gi = g + (uint32_t)k;
+                            mbar_wait(&full_b[gi % (uint32_t)n_stages], (gi / (uint32_t)n_stages) & 1u);
+                        }
+                        tc_fence_after();
+                        for (int uu = 0; uu < kUT; ++uu) {
+                            mbar_wait(&tmem_empty[uu * 2 + acc], acc_phase ^ 1);
+                            tc_fence_after();
+                            const uint32_t d_tmem = tmem_base + (uint32_t)(uu * 2 + acc) * kSN;
+                            for (int k = 0; k < n_atoms; ++k) {
+                                const uint32_t a_base = smem_u32(sm_a + (size_t)(uu * n_atoms + k) * kAtomBytes);
+                                const uint32_t b_base =
+                                    smem_u32(sm_b + (size_t)((g + (uint32_t)k) % (uint32_t)n_stages) * kAtomBytes);
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk)
+                                    tc_mma_bf16(d_tmem, umma_desc_sw128(a_base + kk * 32),
+                                                umma_desc_sw128(b_base + kk * 32), idesc, (k | kk) ? 1u : 0u);
+                            }
+                            tc_commit(&tmem_full[uu * 2 + acc]);
+                        }
+                        for (int k = 0; k < n_atoms; ++k) tc_commit(&empty_b[(g + (uint32_t)k) % (uint32_t)n_stages]);
+                        g += (uint32_t)n_atoms;
+                    }
+                }
+            } else {
+                // ===== epilogue: thread = user row; warp % 4 = TMEM lane quarter =====
+                for (int i2 = it; i2 < seg_end; ++i2, ++t) {
+                    const uint32_t acc = t & 1u, acc_phase = (t >> 1) & 1u;
+                    const int i0 = i2 * kSN;
+                    st_tiles += 1;
+                    mbar_wait(&tmem_full[u * 2 + acc], acc_phase);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(u * 2 + acc) * kSN;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < kSN; c0 += 32) {
+                        uint32_t v[32];
+                        tc_ld_32x32(taddr + c0, v);
+                        tc_ld_wait();
+                        if (a.debug == 1) continue;
+                        const int cbase = i0 + c0;
+                        const float nbi = a.nb[cbase + lane];  // this lane's column (nb is padded to the tile grid)
+                        if (HAS_BIAS) {
+                            const int item = a.perm[cbase + lane];
+                            const float bl = (item >= 0) ? a.bias[item] : 0.f;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                v[j] = __float_as_uint(fmaf(__shfl_sync(0xffffffffu, bl, j), rc.sc, __uint_as_float(v[j])));
+                        }
+                        float m0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
+                        float m1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
+#pragma unroll
+                        for (int j = 4; j < 32; j += 4) {
+                            m0 = fmaxf(fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), m0);
+                            m1 = fmaxf(fmaxf(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), m1);
+                        }
+                        // ub of the chunk's best column >= L ?   (norms descend: the chunk's largest norm is column 0's)
+                        const float nbc = __shfl_sync(0xffffffffu, nbi, 0);
+                        const bool flag = fmaxf(m0, m1) + fmaf(rc.ce, nbc, rc.ab) >= L;
+                        const unsigned f = __ballot_sync(0xffffffffu, flag);
+                        if (f == 0u || a.debug == 2) continue;
+                        // ---- slow path (warp-cooperative append; lane = column) ----
+                        st_slow += 1;
+                        if (flag) {
+#pragma unroll
+                            for (int j8 = 0; j8 < 8; ++j8) {
+                                float4 w;
+                                w.x = __uint_as_float(v[4 * j8 + 0]);
+                                w.y = __uint_as_float(v[4 * j8 + 1]);
+                                w.z = __uint_as_float(v[4 * j8 + 2]);
+                                w.w = __uint_as_float(v[4 * j8 + 3]);
+                                *reinterpret_cast<float4*>(strip + lane * 32 + ((j8 ^ (lane & 7)) << 2)) = w;
+                            }
+                        }
+                        const bool col_ok = cbase + lane < a.I;
+                        __syncwarp();
+                        unsigned ff = f;
+                        while (ff) {
+                            const int l = __ffs(ff) - 1;
+                            ff &= ff - 1;
+                            const float s = strip[l * 32 + (((lane >> 2) ^ (l & 7)) << 2) + (lane & 3)];
+                            const float L_l = __shfl_sync(0xffffffffu, L, l);
+                            const float ce_l = __shfl_sync(0xffffffffu, rc.ce, l);
+                            const float ab_l = __shfl_sync(0xffffffffu, rc.ab, l);
+                            const int cnt_l = __shfl_sync(0xffffffffu, cnt, l);
+                            const bool take = (s + fmaf(ce_l, nbi, ab_l) >= L_l) && col_ok;
+                            const unsigned tb = __ballot_sync(0xffffffffu, take);
+                            if (take)
+                                cta_slots[(int64_t)(warp_row0 + l) * CAP + cnt_l + __popc(tb & lt_mask)] =
+                                    ((uint64_t)f32_to_ordered(s) << 32) | (uint32_t)(cbase + lane);
+                            const int n = __popc(tb);
+                            if (lane == l) cnt += n;
+                            st_app += n;
+                        }
+                        __syncwarp();
+                        unsigned need = __ballot_sync(0xffffffffu, cnt >= TRIG);
+                        while (need) {
+                            const int l = __ffs(need) - 1;
+                            need &= need - 1;
+                            const PruneResult pr = screen_prune<NPL>(
+                                cta_slots + (int64_t)(warp_row0 + l) * CAP, __shfl_sync(0xffffffffu, cnt, l),
+                                __shfl_sync(0xffffffffu, chk, l), __shfl_sync(0xffffffffu, rc.ce, l),
+                                __shfl_sync(0xffffffffu, rc.ab, l), a.nb, a.perm, a.mask_items,
+                                __shfl_sync(0xffffffffu, mlo, l), __shfl_sync(0xffffffffu, mhi, l), a.K, lane, a.stats);
+                            if (lane == l) {
+                                cnt = pr.cnt;
+                                chk = pr.cnt;
+                                L = fmaxf(L, pr.lbK);
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&tmem_empty[u * 2 + acc]);
+                }
+            }
+            it = seg_end;
+            if (it < it_end) {
+                // ---- checkpoint: how many tiles do this CTA's rows still need? ----
+                if (warp >= 2 && a.debug == 0) {
+                    // tighten every live row's L first (a prune needs >= K keys to say anything)
+                    for (int l = 0; l < 32; ++l) {
+                        const int cnt_l = __shfl_sync(0xffffffffu, cnt, l);
+                        if (cnt_l < a.K) continue;  // warp-uniform
+                        const PruneResult pr = screen_prune<NPL>(
+                            cta_slots + (int64_t)(warp_row0 + l) * CAP, cnt_l, __shfl_sync(0xffffffffu, chk, l),
+                            __shfl_sync(0xffffffffu, rc.ce, l), __shfl_sync(0xffffffffu, rc.ab, l), a.nb, a.perm,
+                            a.mask_items, __shfl_sync(0xffffffffu, mlo, l), __shfl_sync(0xffffffffu, mhi, l), a.K, lane,
+                            a.stats);
+                        if (lane == l) {
+                            cnt = pr.cnt;
+                            chk = pr.cnt;
+                            L = fmaxf(L, pr.lbK);
+                        }
+                    }
+                    // smallest tile index j >= it with  |u| * nb[j * 128] (+ bias) < L : tiles [it, j) still matter
+                    int lo = it, hi = it_end;
+                    if (L == INFINITY) {
+                        hi = it;  // finished / dead / padding row
+                    } else if (L > -INFINITY) {
+                        const float bt = HAS_BIAS ? rc.sc * bias_abs_max : 0.f;
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            if (fmaf(rc.na, a.nb[(int64_t)mid * kSN], bt) * 1.000001f < L)
+                                hi = mid;
+                            else
+                                lo = mid + 1;
+                        }
+                    }
+                    int need_tiles = hi;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) need_tiles = max(need_tiles, __shfl_xor_sync(0xffffffffu, need_tiles, o));
+                    if (lane == 0) atomicMax(sm_need, need_tiles);
+                } else if (warp >= 2 && lane == 0) {
+                    atomicMax(sm_need, it_end);
+                }
+                __syncthreads();
+                const int agreed = *sm_need;
+                __syncthreads();
+                if (threadIdx.x == 0) *sm_need = 0;
+                if (agreed < it_end) it_end = agreed > it ? agreed : it;
+                if (a.debug == 3) it_end = n_itiles;
+                next_check = next_check * 2;
+            }
+        }
+
+        // ---- group epilogue ----
+        if (warp == 1) {
+            if (lane == 0) tc_commit(a_empty);  // A' tiles free once every MMA of this group retired
+        } else if (warp >= 2 && (a.debug == 0 || a.debug == 3)) {
+            // prune, exact re-score, sort, write (the warp walks its 32 rows)
+            for (int l = 0; l < 32; ++l) {
+                const int64_t rb = (int64_t)ug * kRowsPerCta + warp_row0 + l;
+                if (rb >= a.B) break;  // rows are contiguous: warp-uniform exit
+                int cnt_l = __shfl_sync(0xffffffffu, cnt, l);
+                bool fallback = __shfl_sync(0xffffffffu, (int)force_exact, l) != 0 || cnt_l < a.K;
+                uint64_t* s_row = cta_slots + (int64_t)(warp_row0 + l) * CAP;
+                if (!fallback) {
+                    const PruneResult pr = screen_prune<NPL>(
+                        s_row, cnt_l, __shfl_sync(0xffffffffu, chk, l), __shfl_sync(0xffffffffu, rc.ce, l),
+                        __shfl_sync(0xffffffffu, rc.ab, l), a.nb, a.perm, a.mask_items, __shfl_sync(0xffffffffu, mlo, l),
+                        __shfl_sync(0xffffffffu, mhi, l), a.K, lane, a.stats);
+                    cnt_l = pr.cnt;
+                    fallback = cnt_l < a.K;  // overflow (-1) or too few unmasked candidates
+                }
+                if (!fallback) {
+                    const float* urow = a.Eu + (a.users ? a.users[rb] : rb) * a.lde_u;
+                    st_resc += cnt_l;
+                    if (cnt_l <= 64)
+                        rescore_sort_write<2>(a, urow, s_row, cnt_l, lane, rb);
+                    else if (cnt_l <= 128)
+                        rescore_sort_write<4>(a, urow, s_row, cnt_l, lane, rb);
+                    else
+                        rescore_sort_write<NPL>(a, urow, s_row, cnt_l, lane, rb);
+                } else if (lane == 0) {
+                    a.fallback_rows[atomicAdd(a.fallback_count, 1)] = (int32_t)rb;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (warp >= 2 && a.stats != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) st_app += __shfl_xor_sync(0xffffffffu, st_app, o);
+        if (lane == 0) {
+            atomicAdd(&a.stats[0], st_slow);
+            atomicAdd(&a.stats[1], st_app / 32);  // every lane counted each append
+            atomicAdd(&a.stats[5], st_resc);
+            if (ew == 0) atomicAdd(&a.stats[6], st_tiles);  // item tiles swept, summed over user groups
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn scr_encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// [rows, kd] fp16 row-major, boxes of 64 (K) x 128 rows, 128-byte swizzle
+static bool scr_make_map(CUtensorMap* m, void* base, int64_t rows, int64_t kd)
+{
+    EncodeTiledFn fn = scr_encode_fn();
+    if (fn == nullptr) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)kd, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)kd * 2};
+    cuuint32_t box[2] = {64, 128};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int scr_npl(int32_t K) { return K <= 64 ? 8 : (K <= 128 ? 16 : 32); }
+
+static size_t scr_smem_fixed(int32_t D)
+{
+    return (size_t)kUT * (D / 64) * kAtomBytes + (size_t)kEpiWarps * 4096 + (2 * kScrMaxStages + 12) * sizeof(uint64_t) + 1024;
+}
+static int scr_stages(int32_t D)
+{
+    const int64_t room = (int64_t)227 * 1024 - (int64_t)scr_smem_fixed(D);
+    const int s = (int)(room / kAtomBytes);
+    return s > kScrMaxStages ? kScrMaxStages : s;
+}
+
+bool score_screen_supported(int32_t D, int32_t K)
+{
+    return D % 64 == 0 && D >= 64 && D <= 256 && K >= 1 && K <= 256 && scr_stages(D) >= D / 64;
+}
+
+static int scr_grid(int32_t B)
+{
+    const int groups = (B + kRowsPerCta - 1) / kRowsPerCta;
+    return groups < sm_count() ? groups : sm_count();
+}
+
+static size_t scr_sort_temp_bytes(int32_t I)
+{
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                              (const int32_t*)nullptr, (int32_t*)nullptr, I);
+    return bytes;
+}
+
+struct ScrLayout {
+    int64_t a_h, b_h, row_const, nb, perm, nb_raw, ident, sort_tmp, misc, fallback, slots, simt, total;
+    int64_t sort_tmp_bytes;
+    int32_t b_pad, i_pad;
+};
+
+static ScrLayout scr_layout(int32_t B, int32_t I, int32_t D, int32_t K)
+{
+    ScrLayout L;
+    L.b_pad = (B + kRowsPerCta - 1) / kRowsPerCta * kRowsPerCta;
+    L.i_pad = (I + kSN - 1) / kSN * kSN;
+    const int cap = 32 * scr_npl(K);
+    int64_t off = 0;
+    auto take = [&](int64_t bytes) {
+        const int64_t o = off;
+        off += align_up(bytes, 256);
+        return o;
+    };
+    L.a_h = take((int64_t)L.b_pad * D * 2);
+    L.b_h = take((int64_t)L.i_pad * D * 2);
+    L.row_const = take((int64_t)L.b_pad * sizeof(RowConst));
+    L.nb = take((int64_t)L.i_pad * 4);
+    L.perm = take((int64_t)L.i_pad * 4);
+    L.nb_raw = take((int64_t)L.i_pad * 4);
+    L.ident = take((int64_t)L.i_pad * 4);
+    L.sort_tmp_bytes = (int64_t)scr_sort_temp_bytes(I);
+    L.sort_tmp = take(L.sort_tmp_bytes);
+    L.misc = take(256);  // u32 [0] item absmax bits, [1] fallback count, [3] bias absmax; u64 stats at +64
+    L.fallback = take((int64_t)B * 4);
+    L.slots = take((int64_t)scr_grid(B) * kRowsPerCta * cap * 8);
+    L.simt = take(score_simt_workspace_bytes(B, K));
+    L.total = off;
+    return L;
+}
+
+int64_t score_screen_workspace_bytes(int32_t B, int32_t I, int32_t D, int32_t K) { return scr_layout(B, I, D, K).total; }
+
+int score_screen_fallback_count(const void* workspace, int32_t B, int32_t I, int32_t D, int32_t K, int32_t* count_host,
+                                cudaStream_t st)
+{
+    const ScrLayout L = scr_layout(B, I, D, K);
+    GMR_CHECK_CUDA(cudaMemcpyAsync(count_host, (const uint8_t*)workspace + L.misc + 4, sizeof(int32_t),
+                                   cudaMemcpyDeviceToHost, st));
+    GMR_CHECK_CUDA(cudaStreamSynchronize(st));
+    return GMR_OK;
+}
+
+// diagnostics of the last call with GMR_SCREEN_STATS=1: [0] slow-path chunks, [1] appends, [2] pool prunes,
+// [3] exact prunes, [5] exactly re-scored candidates, [6] item tiles swept (summed over 256-user groups)
+int score_screen_stats(const void* workspace, int32_t B, int32_t I, int32_t D, int32_t K, uint64_t* stats_host,
+                       cudaStream_t st)
+{
+    const ScrLayout L = scr_layout(B, I, D, K);
+    GMR_CHECK_CUDA(cudaMemcpyAsync(stats_host, (const uint8_t*)workspace + L.misc + 64, kStatSlots * sizeof(uint64_t),
+                                   cudaMemcpyDeviceToHost, st));
+    GMR_CHECK_CUDA(cudaStreamSynchronize(st));
+    return GMR_OK;
+}
+
+int score_topk_screen_launch(const float* Eu, int64_t lde_u, const int64_t* users, int32_t B, const float* Ei,
+                             int64_t lde_i, const float* bias, int32_t I, int32_t D, const int64_t* mask_rowptr,
+                             const int32_t* mask_items, int32_t K, int32_t* out_ids, float* out_scores, void* workspace,
+                             int64_t workspace_bytes, cudaStream_t st)
+{
+    const ScrLayout L = scr_layout(B, I, D, K);
+    if (workspace_bytes < L.total) {
+        set_error("score_topk_screen: workspace of %lld bytes required, %lld given", (long long)L.total,
+                  (long long)workspace_bytes);
+        return GMR_ERR_WORKSPACE;
+    }
+    if ((uintptr_t)workspace % 256 != 0) {
+        set_error("score_topk_screen: workspace must be 256-byte aligned");
+        return GMR_ERR_INVALID;
+    }
+    const int n_stages = scr_stages(D);
+    const size_t smem = scr_smem_fixed(D) + (size_t)n_stages * kAtomBytes;
+    uint8_t* ws = (uint8_t*)workspace;
+    __half* a_h = (__half*)(ws + L.a_h);
+    __half* b_h = (__half*)(ws + L.b_h);
+    RowConst* row_const = (RowConst*)(ws + L.row_const);
+    float* nb = (float*)(ws + L.nb);
+    int32_t* perm = (int32_t*)(ws + L.perm);
+    uint32_t* nb_raw = (uint32_t*)(ws + L.nb_raw);
+    int32_t* ident = (int32_t*)(ws + L.ident);
+    uint32_t* misc = (uint32_t*)(ws + L.misc);
+    int32_t* fallback = (int32_t*)(ws + L.fallback);
+
+    GMR_CHECK_CUDA(cudaMemsetAsync(misc, 0, 256, st));
+    const int wpb = 8;
+    {
+        const int64_t warps = ((int64_t)I + 3) / 4;  // ~4 rows per warp
+        int grid = (int)((warps + wpb - 1) / wpb);
+        if (grid > 16 * sm_count()) grid = 16 * sm_count();
+        if (grid < 1) grid = 1;
+        absmax_kernel<<<grid, wpb * 32, 0, st>>>(Ei, lde_i, I, D, misc);
+        GMR_LAUNCH_CHECK();
+        if (bias != nullptr) {
+            absmax_kernel<<<grid, wpb * 32, 0, st>>>(bias, 1, I, 1, misc + 3);
+            GMR_LAUNCH_CHECK();
+        }
+    }
+    item_norms_kernel<<<(I + wpb - 1) / wpb, wpb * 32, 0, st>>>(Ei, lde_i, I, D, misc, nb_raw, ident);
+    GMR_LAUNCH_CHECK();
+    {
+        size_t tmp = (size_t)L.sort_tmp_bytes;
+        GMR_CHECK_CUDA(cub::DeviceRadixSort::SortPairsDescending(ws + L.sort_tmp, tmp, nb_raw, (uint32_t*)nb, ident, perm, I,
+                                                                 0, 32, st));
+    }
+    prep_items_kernel<<<(L.i_pad + wpb - 1) / wpb, wpb * 32, 0, st>>>(Ei, lde_i, I, L.i_pad, D, misc, perm, nb, b_h);
+    GMR_LAUNCH_CHECK();
+    prep_users_kernel<<<(L.b_pad + wpb - 1) / wpb, wpb * 32, 0, st>>>(Eu, lde_u, users, B, L.b_pad, D, misc, nb,
+                                                                     bias ? misc + 3 : nullptr, a_h, row_const);
+    GMR_LAUNCH_CHECK();
+
+    CUtensorMap map_a, map_b;
+    if (!scr_make_map(&map_a, a_h, L.b_pad, D) || !scr_make_map(&map_b, b_h, L.i_pad, D)) {
+        set_error("score_topk_screen: cuTensorMapEncodeTiled unavailable or failed");
+        return GMR_ERR_CUDA;
+    }
+    ScrArgs a;
+    a.Eu = Eu; a.lde_u = lde_u; a.users = users; a.B = B; a.Ei = Ei; a.lde_i = lde_i; a.bias = bias; a.I = I; a.D = D;
+    a.mask_rowptr = mask_rowptr; a.mask_items = mask_items; a.K = K; a.out_ids = out_ids; a.out_scores = out_scores;
+    a.slots = (uint64_t*)(ws + L.slots); a.row_const = row_const; a.nb = nb; a.perm = perm;
+    a.biasmax_bits = bias ? misc + 3 : nullptr;
+    a.fallback_rows = fallback; a.fallback_count = (int32_t*)(misc + 1); a.n_stages = n_stages;
+    a.vec4 = ((lde_u % 4 == 0) && (lde_i % 4 == 0) && ((uintptr_t)Eu % 16 == 0) && ((uintptr_t)Ei % 16 == 0)) ? 1 : 0;
+    a.first_check = (2 * K + kSN - 1) / kSN;  // enough tiles for ~2K candidates before the first stop check
+    a.stats = getenv("GMR_SCREEN_STATS") ? (unsigned long long*)(ws + L.misc + 64) : nullptr;
+    a.debug = getenv("GMR_TC_DEBUG") ? atoi(getenv("GMR_TC_DEBUG")) : 0;
+    const int grid = scr_grid(B);
+    const int npl = scr_npl(K);
+#define GMR_SCR_LAUNCH(NPL)                                                                                        \
+    do {                                                                                                           \
+        if (bias != nullptr) {                                                                                     \
+            GMR_CHECK_CUDA(cudaFuncSetAttribute(score_screen_kernel<NPL, true>,                                    \
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+            score_screen_kernel<NPL, true><<<grid, kScrThreads, smem, st>>>(map_a, map_b, a);                      \
+        } else {                                                                                                   \
+            GMR_CHECK_CUDA(cudaFuncSetAttribute(score_screen_kernel<NPL, false>,                                   \
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+            score_screen_kernel<NPL, false><<<grid, kScrThreads, smem, st>>>(map_a, map_b, a);                     \
+        }                                                                                                          \
+    } while (0)
+    if (npl == 8)
+        GMR_SCR_LAUNCH(8);
+    else if (npl == 16)
+        GMR_SCR_LAUNCH(16);
+    else
+        GMR_SCR_LAUNCH(32);
+#undef GMR_SCR_LAUNCH
+    GMR_LAUNCH_CHECK();
+    // queued rows: exact fp32 kernel, row count read on the device (no host synchronisation)
+    score_simt_set_dynamic_rows((const int32_t*)(misc + 1));
+    const int fb_grid = 2 * sm_count() < (B + 127) / 128 ? 2 * sm_count() : (B + 127) / 128;
+    const int rc = score_topk_simt_launch(Eu, lde_u, users, fallback, B, Ei, lde_i, bias, I, D, mask_rowptr, mask_items, K,
+                                          out_ids, out_scores, ws + L.simt, st, fb_grid);
+    score_simt_set_dynamic_rows(nullptr);
+    return rc;
+}
+
+}  // namespace gmr

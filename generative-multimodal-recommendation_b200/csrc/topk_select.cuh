@@ -30,8 +30,8 @@ __device__ __forceinline__ int32_t key_id(uint64_t k) { return (int32_t)(0xFFFFF
 __device__ __forceinline__ float key_score(uint64_t k) { return ordered_to_f32((uint32_t)(k >> 32)); }
 
 // Sort 32 * NPL keys held as k[r] = element (r * 32 + lane), descending (element 0 = largest).
-template <int NPL>
-__device__ __forceinline__ void warp_bitonic_sort_desc(uint64_t (&k)[NPL], int lane)
+template <int NPL, typename T = uint64_t>
+__device__ __forceinline__ void warp_bitonic_sort_desc(T (&k)[NPL], int lane)
 {
     constexpr int N = 32 * NPL;
 #pragma unroll
@@ -42,12 +42,12 @@ __device__ __forceinline__ void warp_bitonic_sort_desc(uint64_t (&k)[NPL], int l
 #pragma unroll
                 for (int r = 0; r < NPL; ++r) {
                     const int i = r * 32 + lane;
-                    const uint64_t other = __shfl_xor_sync(0xffffffffu, k[r], stride);
+                    const T other = __shfl_xor_sync(0xffffffffu, k[r], stride);
                     const bool desc = (i & size) == 0;
                     const bool lower = (lane & stride) == 0;
                     const bool take_max = (lower == desc);
-                    const uint64_t mx = k[r] > other ? k[r] : other;
-                    const uint64_t mn = k[r] > other ? other : k[r];
+                    const T mx = k[r] > other ? k[r] : other;
+                    const T mn = k[r] > other ? other : k[r];
                     k[r] = take_max ? mx : mn;
                 }
             } else {
@@ -60,9 +60,9 @@ __device__ __forceinline__ void warp_bitonic_sort_desc(uint64_t (&k)[NPL], int l
                         const int r2 = r | rs;
                         const int i = r * 32 + lane;
                         const bool desc = (i & size) == 0;
-                        const uint64_t a = k[r], b = k[r2];
-                        const uint64_t mx = a > b ? a : b;
-                        const uint64_t mn = a > b ? b : a;
+                        const T a = k[r], b = k[r2];
+                        const T mx = a > b ? a : b;
+                        const T mn = a > b ? b : a;
                         k[r] = desc ? mx : mn;
                         k[r2] = desc ? mn : mx;
                     }

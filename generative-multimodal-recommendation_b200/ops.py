@@ -238,9 +238,14 @@ def rows_axpby_norm(x, y=None, z=None, a=1.0, b=0.0, c=0.0, eps=1e-12, out=None)
     return out
 
 
-def tc_supported(d, k):
-    """Shapes the tcgen05 scoring path accepts (A' tile + >= 2 ring stages must fit in shared memory)."""
-    return d % 64 == 0 and 64 <= d <= 192 and k <= 248
+def tc_supported(d, k, precision="tc"):
+    """Shapes the tcgen05 scoring paths accept (operand tiles + ring stages must fit in shared memory)."""
+    if precision == "tc_split":
+        return d % 64 == 0 and 64 <= d <= 192 and k <= 248
+    return d % 64 == 0 and 64 <= d <= 256 and k <= 256
+
+
+_PRECISIONS = {"fp32": _lib.GMR_SCORE_FP32, "tc": _lib.GMR_SCORE_TC, "tc_split": _lib.GMR_SCORE_TC_SPLIT}
 
 
 def score_mask_topk(eu, ei, k, users=None, bias=None, mask_rowptr=None, mask_items=None, precision="fp32",
@@ -255,7 +260,7 @@ def score_mask_topk(eu, ei, k, users=None, bias=None, mask_rowptr=None, mask_ite
     lib = _lib.load()
     if precision == "auto":  # tensor cores whenever the shape is supported; both paths return the same result
         precision = "tc" if tc_supported(int(ei.shape[1]), k) else "fp32"
-    mode = {"fp32": _lib.GMR_SCORE_FP32, "tc": _lib.GMR_SCORE_TC}[precision]
+    mode = _PRECISIONS[precision]
     eup, lde_u = _rows(eu, "eu")
     eip, lde_i = _rows(ei, "ei")
     if eu.shape[1] != ei.shape[1]:
@@ -281,7 +286,9 @@ def score_mask_topk(eu, ei, k, users=None, bias=None, mask_rowptr=None, mask_ite
                                                _ptr(mask_rowptr), _ptr(mask_items), k, mode, _ptr(ids), _ptr(scores),
                                                _ptr(ws), need, _stream()), "gmr_score_mask_topk_f32")
         _prof_end("score_topk", ev, flops=2.0 * b * i * d, users=b, items=i, d=d, k=k, precision=precision)
-    LAUNCHES += 1 if mode == _lib.GMR_SCORE_FP32 else 4  # tc: 2 split kernels + fused kernel + fp32 redo
+    # own kernels only (the cub radix sort of the item norms is library code and not counted):
+    # tc: absmax + item norms + 2 operand-prep kernels + fused kernel + fp32 redo; tc_split: 2 split kernels + fused + redo
+    LAUNCHES += {_lib.GMR_SCORE_FP32: 1, _lib.GMR_SCORE_TC: 6 + (1 if bias is not None else 0), _lib.GMR_SCORE_TC_SPLIT: 4}[mode]
     global _last_score_call
     _last_score_call = (ws, b, i, d, k, mode)
     return ids, scores
@@ -293,13 +300,25 @@ _last_score_call = None
 def last_tc_fallback_rows():
     """Rows of the most recent ``precision='tc'`` call that were redone on the exact fp32 path because
     their candidate margin could not certify exactness (diagnostic; synchronises)."""
-    if _last_score_call is None or _last_score_call[5] != _lib.GMR_SCORE_TC:
+    if _last_score_call is None or _last_score_call[5] == _lib.GMR_SCORE_FP32:
         return 0
-    ws, b, i, d, k, _ = _last_score_call
+    ws, b, i, d, k, mode = _last_score_call
     out = C.c_int32(0)
-    _lib.check(_lib.load().gmr_score_tc_fallback_rows(_ptr(ws), b, i, d, k, C.byref(out), _stream()),
+    _lib.check(_lib.load().gmr_score_tc_fallback_rows(_ptr(ws), b, i, d, k, mode, C.byref(out), _stream()),
                "gmr_score_tc_fallback_rows")
     return int(out.value)
+
+
+def last_tc_stats():
+    """Counters of the most recent ``precision='tc'`` call (all zero unless GMR_SCREEN_STATS is set in the
+    environment): append-path chunks, appended candidates, cheap/exact prunes, re-scored candidates."""
+    if _last_score_call is None or _last_score_call[5] != _lib.GMR_SCORE_TC:
+        return {}
+    ws, b, i, d, k, _ = _last_score_call
+    out = (C.c_uint64 * 8)()
+    _lib.check(_lib.load().gmr_score_tc_stats(_ptr(ws), b, i, d, k, out, _stream()), "gmr_score_tc_stats")
+    return {"slow_chunks": out[0], "appends": out[1], "cheap_prunes": out[2], "exact_prunes": out[3],
+            "rescored": out[5], "tiles_swept": out[6]}
 
 
 def scores_dense(eu, ei, users=None, bias=None):

@@ -98,15 +98,21 @@ int gmr_spmm_csr_f32_push(const gmr_spmm_plan_t* plan, const int32_t* rowptr, co
  * users:        int64[B] row ids into Eu, or NULL for rows 0..B-1
  * mask_rowptr:  int64[B+1] (or NULL: no mask), mask_items int32, ascending within each row
  * out_ids:      int32[B, K]   out_scores: fp32[B, K] or NULL
- * precision:    GMR_SCORE_FP32    CUDA-core fp32 FMA scoring
- *               GMR_SCORE_TC      tcgen05 split-bf16 scoring + exact fp32 re-scoring of the K'
- *                                 best candidates; rows whose candidate margin cannot certify
- *                                 exactness are redone on the fp32 path, so both modes return the
- *                                 same ids.  Requires D % 64 == 0, D <= 256, K <= 248.
+ * precision:    GMR_SCORE_FP32      CUDA-core fp32 FMA scoring
+ *               GMR_SCORE_TC        one fp16 tcgen05 pass used as a certified screen (error bound
+ *                                   2^-10 |u| max|e|), then exact fp32 re-scoring of every item that
+ *                                   can still reach the top K; rows the screen cannot decide (buffer
+ *                                   overflow under massive near-ties, fewer than K unmasked items,
+ *                                   non-finite scores) are redone on the fp32 path.  Same ids and
+ *                                   scores as GMR_SCORE_FP32.  Requires D % 64 == 0, D <= 256.
+ *               GMR_SCORE_TC_SPLIT  first-generation path: 3-term split-bf16 tcgen05 product + exact
+ *                                   re-scoring of the K' best candidates, certified per row.  Same
+ *                                   results; kept for cross-checks.  D % 64 == 0, D <= 192, K <= 248.
  * 1 <= K <= GMR_MAX_TOPK; if fewer than K items exist the tail is (-1, -inf).
  * ------------------------------------------------------------------------------------------- */
 #define GMR_SCORE_FP32 0
 #define GMR_SCORE_TC 1
+#define GMR_SCORE_TC_SPLIT 2
 
 int64_t gmr_score_topk_workspace_bytes(int32_t B, int32_t I, int32_t D, int32_t K, int32_t precision);
 
@@ -115,11 +121,16 @@ int gmr_score_mask_topk_f32(const float* Eu, int64_t lde_u, const int64_t* users
                             const int32_t* mask_items, int32_t K, int32_t precision, int32_t* out_ids,
                             float* out_scores, void* workspace, int64_t workspace_bytes, void* stream);
 
-/* Diagnostics of the last GMR_SCORE_TC call that used `workspace` with the same shape: number of rows
- * whose exactness could not be certified from the candidate margin (they were redone on the fp32
- * path).  Copies one int to the host and synchronises `stream`. */
-int gmr_score_tc_fallback_rows(const void* workspace, int32_t B, int32_t I, int32_t D, int32_t K,
+/* Diagnostics of the last tensor-core call that used `workspace` with the same shape and precision:
+ * number of rows that were redone on the fp32 path.  Copies one int to the host and synchronises
+ * `stream`. */
+int gmr_score_tc_fallback_rows(const void* workspace, int32_t B, int32_t I, int32_t D, int32_t K, int32_t precision,
                                int32_t* count_host, void* stream);
+/* Counters of the last GMR_SCORE_TC call made with the environment variable GMR_SCREEN_STATS set
+ * (zeros otherwise): stats_host[8] = {chunks that took the append path, appended candidates, cheap
+ * prunes, exact prunes, -, exactly re-scored candidates, -, -}.  Synchronises `stream`. */
+int gmr_score_tc_stats(const void* workspace, int32_t B, int32_t I, int32_t D, int32_t K, uint64_t* stats_host,
+                       void* stream);
 
 /* Dense variant for API parity with full_sort_predict (GenMMRec/src/models/diffmm.py:277): writes the
  * fp32 [B, I] score matrix (leading dimension ldo) with the same fmaf chain.  Not used by the fused

@@ -200,10 +200,14 @@ def test_errors_are_loud(ops):
         ops.score_mask_topk(torch.zeros((4, 64), device="cuda"), torch.zeros((9, 64), device="cuda"), 1000)
 
 
-# ---- tensor-core scoring path (tcgen05 split-bf16 + exact re-rank): must equal the fp32 path ----------
+# ---- tensor-core scoring paths: must equal the fp32 path bit for bit -----------------------------------
+#   "tc"        one fp16 tcgen05 pass as a certified screen + exact fp32 re-score (score_topk_screen.cu)
+#   "tc_split"  3-term split-bf16 tcgen05 product + certified exact re-rank       (score_topk_tc.cu)
+
+TC_MODES = ["tc", "tc_split"]
 
 
-def _tc_case(ops, rng, n_users, b, n_items, d, k, with_bias, mask_avg, scale=1.0):
+def _tc_case(ops, rng, n_users, b, n_items, d, k, with_bias, mask_avg, scale=1.0, precision="tc"):
     eu = (rng.standard_normal((n_users, d)) * scale).astype(np.float32)
     ei = (rng.standard_normal((n_items, d)) * scale).astype(np.float32)
     users = rng.choice(n_users, size=b, replace=False).astype(np.int64)
@@ -213,7 +217,7 @@ def _tc_case(ops, rng, n_users, b, n_items, d, k, with_bias, mask_avg, scale=1.0
                 mask_rowptr=torch.from_numpy(mrp).cuda(), mask_items=torch.from_numpy(mit).cuda())
     eu_t, ei_t = torch.from_numpy(eu).cuda(), torch.from_numpy(ei).cuda()
     ids_f, sc_f = ops.score_mask_topk(eu_t, ei_t, k, precision="fp32", **args)
-    ids_t, sc_t = ops.score_mask_topk(eu_t, ei_t, k, precision="tc", **args)
+    ids_t, sc_t = ops.score_mask_topk(eu_t, ei_t, k, precision=precision, **args)
     torch.cuda.synchronize()
     return ids_f.cpu().numpy(), sc_f.cpu().numpy(), ids_t.cpu().numpy(), sc_t.cpu().numpy(), ops.last_tc_fallback_rows()
 
@@ -221,15 +225,111 @@ def _tc_case(ops, rng, n_users, b, n_items, d, k, with_bias, mask_avg, scale=1.0
 @pytest.mark.parametrize("n_items,d,k,with_bias", [(7050, 64, 50, False), (1000, 64, 20, False), (333, 64, 5, True),
                                                    (5000, 128, 50, False), (2100, 192, 50, True), (130, 64, 50, False),
                                                    (4000, 64, 100, False), (3000, 128, 10, True)])
-def test_score_tc_equals_fp32(ops, n_items, d, k, with_bias):
+@pytest.mark.parametrize("precision", TC_MODES)
+def test_score_tc_equals_fp32(ops, n_items, d, k, with_bias, precision):
     rng = np.random.default_rng(1000 + n_items + d)
-    ids_f, sc_f, ids_t, sc_t, fb = _tc_case(ops, rng, 900, 517, n_items, d, k, with_bias, 25)
+    ids_f, sc_f, ids_t, sc_t, fb = _tc_case(ops, rng, 900, 517, n_items, d, k, with_bias, 25, precision=precision)
     assert np.array_equal(ids_t, ids_f)
     assert np.array_equal(sc_t, sc_f)
     assert fb <= 0.02 * 517  # certification almost never fails on continuous random scores
 
 
-def test_score_tc_matches_oracle_bit_exact(ops):
+@pytest.mark.parametrize("n_users,b,n_items,d,k,with_bias", [(300, 300, 3000, 256, 50, True), (2000, 1300, 9000, 64, 200, False),
+                                                             (64, 7, 100, 64, 50, False), (700, 600, 20000, 64, 256, False),
+                                                             (1024, 1024, 4096, 128, 64, False)])
+def test_score_screen_shapes(ops, n_users, b, n_items, d, k, with_bias):
+    """Shapes only the screen path takes: D = 256, K up to 256, fewer users than one CTA group, fewer items
+    than one tile, exact multiples of the tile sizes."""
+    rng = np.random.default_rng(4000 + n_items + d + k)
+    ids_f, sc_f, ids_t, sc_t, fb = _tc_case(ops, rng, n_users, b, n_items, d, k, with_bias, 10, precision="tc")
+    assert np.array_equal(ids_t, ids_f)
+    assert np.array_equal(sc_t, sc_f)
+
+
+def test_score_screen_all_equal_items_overflow(ops):
+    """Every item identical: the screen cannot separate anything, every row overflows its candidate buffer and
+    is redone on the fp32 path; order is then decided by the item id alone."""
+    rng = np.random.default_rng(8)
+    n_items, d, k = 3000, 64, 50
+    ei = np.repeat(rng.standard_normal((1, d)).astype(np.float32), n_items, axis=0)
+    eu = rng.standard_normal((300, d)).astype(np.float32)
+    ids_ref, sc_ref = c_api.score_mask_topk(eu, None, ei, None, None, None, k)
+    ids, sc = ops.score_mask_topk(torch.from_numpy(eu).cuda(), torch.from_numpy(ei).cuda(), k, precision="tc")
+    fb = ops.last_tc_fallback_rows()
+    assert np.array_equal(ids.cpu().numpy(), ids_ref)
+    assert np.array_equal(sc.cpu().numpy(), sc_ref)
+    assert fb == 300
+
+
+def test_score_screen_zero_and_tiny_rows(ops):
+    """All-zero user rows (every score ties at 0), subnormal-scale rows and items next to ordinary ones."""
+    rng = np.random.default_rng(9)
+    n_items, d, k = 2500, 64, 20
+    eu = rng.standard_normal((260, d)).astype(np.float32)
+    eu[3] = 0.0
+    eu[77] *= 1e-30
+    eu[78] *= 1e20
+    ei = rng.standard_normal((n_items, d)).astype(np.float32)
+    ei[5] = 0.0
+    ei[6] *= 1e-12
+    ids_ref, sc_ref = c_api.score_mask_topk(eu, None, ei, None, None, None, k)
+    ids, sc = ops.score_mask_topk(torch.from_numpy(eu).cuda(), torch.from_numpy(ei).cuda(), k, precision="tc")
+    assert np.array_equal(ids.cpu().numpy(), ids_ref)
+    assert np.array_equal(sc.cpu().numpy(), sc_ref)
+
+
+def test_score_screen_skewed_norms_early_stop(ops, monkeypatch):
+    """Popularity-skewed item norms: the norm-ordered sweep must stop long before the catalogue ends (exact
+    Cauchy-Schwarz pruning) and still return the oracle's result; train histories are drawn from the
+    high-norm items so that some rows need more tiles than others."""
+    monkeypatch.setenv("GMR_SCREEN_STATS", "1")
+    rng = np.random.default_rng(11)
+    n_items, d, k, b = 30000, 64, 50, 700
+    scale = np.exp(rng.normal(0.0, 1.2, size=(n_items, 1)))
+    ei = (rng.standard_normal((n_items, d)) * scale).astype(np.float32)
+    eu = rng.standard_normal((b, d)).astype(np.float32)
+    hot = np.argsort(-scale[:, 0])[:600]
+    lens = rng.integers(0, 120, size=b)
+    lens[::50] = 550                                  # a few users have seen almost every popular item
+    rows = [np.sort(rng.choice(hot, size=n, replace=False)).astype(np.int32) for n in lens]
+    mrp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    mit = np.concatenate(rows)
+    ids_ref, sc_ref = c_api.score_mask_topk(eu, None, ei, None, mrp, mit, k)
+    ids, sc = ops.score_mask_topk(torch.from_numpy(eu).cuda(), torch.from_numpy(ei).cuda(), k,
+                                  mask_rowptr=torch.from_numpy(mrp).cuda(), mask_items=torch.from_numpy(mit).cuda(),
+                                  precision="tc")
+    st = ops.last_tc_stats()
+    assert np.array_equal(ids.cpu().numpy(), ids_ref)
+    assert np.array_equal(sc.cpu().numpy(), sc_ref)
+    assert ops.last_tc_fallback_rows() == 0
+    n_groups, full = (b + 255) // 256, (n_items + 127) // 128
+    assert 0 < st["tiles_swept"] < 0.5 * n_groups * full, st
+
+
+def test_score_screen_heavy_mask(ops):
+    """Rows whose train history covers most of the catalogue (fewer than K unmasked items for some): masked
+    items must surface with -1e10 exactly like trainer.py:384."""
+    rng = np.random.default_rng(10)
+    n_items, d, k, b = 400, 64, 50, 270
+    eu = rng.standard_normal((b, d)).astype(np.float32)
+    ei = rng.standard_normal((n_items, d)).astype(np.float32)
+    rowptr = [0]
+    items = []
+    for r in range(b):
+        n = n_items - (r % 80)                      # leaves 0..79 unmasked items
+        items.append(np.sort(rng.choice(n_items, size=n, replace=False)).astype(np.int32))
+        rowptr.append(rowptr[-1] + n)
+    mrp, mit = np.asarray(rowptr, dtype=np.int64), np.concatenate(items)
+    ids_ref, sc_ref = c_api.score_mask_topk(eu, None, ei, None, mrp, mit, k)
+    ids, sc = ops.score_mask_topk(torch.from_numpy(eu).cuda(), torch.from_numpy(ei).cuda(), k,
+                                  mask_rowptr=torch.from_numpy(mrp).cuda(), mask_items=torch.from_numpy(mit).cuda(),
+                                  precision="tc")
+    assert np.array_equal(ids.cpu().numpy(), ids_ref)
+    assert np.array_equal(sc.cpu().numpy(), sc_ref)
+
+
+@pytest.mark.parametrize("precision", TC_MODES)
+def test_score_tc_matches_oracle_bit_exact(ops, precision):
     rng = np.random.default_rng(77)
     n_users, b, n_items, d, k = 400, 300, 2500, 64, 50
     eu = rng.standard_normal((n_users, d)).astype(np.float32)
@@ -239,12 +339,13 @@ def test_score_tc_matches_oracle_bit_exact(ops):
     ids_ref, sc_ref = c_api.score_mask_topk(eu, users, ei, None, mrp, mit, k)
     ids, sc = ops.score_mask_topk(torch.from_numpy(eu).cuda(), torch.from_numpy(ei).cuda(), k,
                                   users=torch.from_numpy(users).cuda(), mask_rowptr=torch.from_numpy(mrp).cuda(),
-                                  mask_items=torch.from_numpy(mit).cuda(), precision="tc")
+                                  mask_items=torch.from_numpy(mit).cuda(), precision=precision)
     assert np.array_equal(ids.cpu().numpy(), ids_ref)
     assert np.array_equal(sc.cpu().numpy(), sc_ref)
 
 
-def test_score_tc_ties_force_exact_fallback(ops):
+@pytest.mark.parametrize("precision", TC_MODES)
+def test_score_tc_ties_force_exact_fallback(ops, precision):
     """Many duplicated items: near/exact ties everywhere, so certification must fail for most rows and
     the fp32 redo must still deliver the oracle's total order (score desc, id asc)."""
     rng = np.random.default_rng(5)
@@ -253,21 +354,24 @@ def test_score_tc_ties_force_exact_fallback(ops):
     ei = base[rng.integers(0, 30, size=n_items)]          # only 30 distinct item vectors
     eu = rng.standard_normal((260, d)).astype(np.float32)
     ids_ref, sc_ref = c_api.score_mask_topk(eu, None, ei, None, None, None, k)
-    ids, sc = ops.score_mask_topk(torch.from_numpy(eu).cuda(), torch.from_numpy(ei).cuda(), k, precision="tc")
+    ids, sc = ops.score_mask_topk(torch.from_numpy(eu).cuda(), torch.from_numpy(ei).cuda(), k, precision=precision)
     fb = ops.last_tc_fallback_rows()
     assert np.array_equal(ids.cpu().numpy(), ids_ref)
     assert np.array_equal(sc.cpu().numpy(), sc_ref)
-    assert fb > 50  # certification fails wherever K-th/KP-th candidates are (near) ties
+    if precision == "tc_split":
+        assert fb > 50  # certification fails wherever K-th/KP-th candidates are (near) ties
+    # the screen keeps every tied candidate (its buffer holds the ~50 copies of each leading vector)
 
 
-def test_score_tc_wide_dynamic_range(ops):
+@pytest.mark.parametrize("precision", TC_MODES)
+def test_score_tc_wide_dynamic_range(ops, precision):
     """Rows and items with norms spread over 4 decades: the error bound scales with the norms."""
     rng = np.random.default_rng(6)
     n_items, d, k = 6000, 64, 50
     eu = (rng.standard_normal((300, d)) * np.exp(rng.uniform(-4, 4, size=(300, 1)))).astype(np.float32)
     ei = (rng.standard_normal((n_items, d)) * np.exp(rng.uniform(-4, 4, size=(n_items, 1)))).astype(np.float32)
     ids_ref, sc_ref = c_api.score_mask_topk(eu, None, ei, None, None, None, k)
-    ids, sc = ops.score_mask_topk(torch.from_numpy(eu).cuda(), torch.from_numpy(ei).cuda(), k, precision="tc")
+    ids, sc = ops.score_mask_topk(torch.from_numpy(eu).cuda(), torch.from_numpy(ei).cuda(), k, precision=precision)
     assert np.array_equal(ids.cpu().numpy(), ids_ref)
     assert np.array_equal(sc.cpu().numpy(), sc_ref)
 
