@@ -221,11 +221,26 @@ __device__ __noinline__ PruneResult screen_prune(uint64_t* __restrict__ s_row, i
         k[r] = (i < cnt) ? s_row[i] : 0ull;
     }
     if (mlo < mhi) {
+        // NPL binary searches in lock-step over the row's ascending train-history list: every step issues NPL
+        // independent loads (branch-free lower bound), so the chain costs log2(len) latencies, not NPL * log2(len)
+        int32_t id[NPL];
+        int64_t base[NPL];
 #pragma unroll
         for (int r = 0; r < NPL; ++r) {
             const int i = r * 32 + lane;
-            if (k[r] != 0ull && i >= n_checked && sorted_contains(mask_items, mlo, mhi, perm[(uint32_t)k[r]])) k[r] = 0ull;
+            id[r] = (k[r] != 0ull && i >= n_checked) ? perm[(uint32_t)k[r]] : -1;  // -1: nothing to look up
+            base[r] = mlo;
         }
+        int64_t len = mhi - mlo;
+        while (len > 1) {
+            const int64_t half = len >> 1;
+#pragma unroll
+            for (int r = 0; r < NPL; ++r) base[r] += (mask_items[base[r] + half - 1] < id[r]) ? half : 0;
+            len -= half;
+        }
+#pragma unroll
+        for (int r = 0; r < NPL; ++r)
+            if (id[r] >= 0 && mask_items[base[r]] == id[r]) k[r] = 0ull;
     }
 #pragma unroll
     for (int r = 0; r < NPL; ++r) {
@@ -321,20 +336,52 @@ struct ScrArgs {
     int32_t K;
     int32_t* out_ids;
     float* out_scores;
-    uint64_t* slots;            // [grid][kRowsPerCta][CAP]
+    uint64_t* slots;            // [B_pad][CAP] candidate keys of every row: (ordered s~) << 32 | sweep position
     const RowConst* row_const;  // [B_pad]
     const float* nb;            // [I_pad] scaled item norms in sweep order (descending, rounded up)
     const int32_t* perm;        // [I_pad] sweep position -> item id (-1: padding)
     const uint32_t* biasmax_bits;
+    // per-row sweep state carried between the kernels of one call
+    int32_t* row_cnt;           // [B_pad] keys in the row's slots; -1: overflowed (fp32 path)
+    int32_t* row_chk;           // [B_pad] leading keys already tested against the train-history mask
+    float* row_L;               // [B_pad] lower bound of the row's exact K-th score; +inf: nothing left to collect
+    int32_t* group_need;        // [n_groups] item tiles the 256-user group still needs (max over its rows)
+    int32_t* work_counter;      // [1] dynamic group scheduler of the continuation sweep
     int32_t* fallback_rows;     // [B]
     int32_t* fallback_count;    // [1]
     int32_t n_stages;
     int32_t vec4;               // Eu / Ei rows are 16-byte aligned
-    int32_t first_check;        // tiles before the first stop check
+    int32_t first_check;        // tiles swept before the first stop check (phase 0)
     unsigned long long* stats;  // [kStatSlots] or null
     int32_t debug;              // GMR_TC_DEBUG timing experiments: 1 = drain TMEM only, 2 = filter without appends,
                                 // 3 = no early stop (full sweep; results stay exact)
 };
+
+__device__ __forceinline__ bool row_force_exact(const ScrArgs& a, int64_t b, int64_t& mlo, int64_t& mhi)
+{
+    mlo = mhi = 0;
+    if (a.mask_rowptr != nullptr) {
+        mlo = a.mask_rowptr[b];
+        mhi = a.mask_rowptr[b + 1];
+    }
+    return (int64_t)a.I - (mhi - mlo) < (int64_t)a.K;  // masked items would surface: the fp32 kernel owns that case
+}
+
+// smallest tile index j in [lo, hi] with  |u| * nb[j * 128] (+ bias bound) < L : tiles [lo, j) can still matter
+__device__ __forceinline__ int tiles_needed(const ScrArgs& a, const RowConst& rc, float L, float bias_abs_max, int lo, int hi)
+{
+    if (L == INFINITY) return lo;   // finished / dead / padding row
+    if (!(L > -INFINITY)) return hi;  // nothing known yet
+    const float bt = rc.sc * bias_abs_max;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (fmaf(rc.na, a.nb[(int64_t)mid * kSN], bt) * 1.000001f < L)
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    return hi;
+}
 
 template <int NSORT>
 __device__ __forceinline__ void final_sort_write(uint64_t (&ek)[NSORT], int lane, const ScrArgs& a, int64_t rb)
@@ -351,45 +398,57 @@ __device__ __forceinline__ void final_sort_write(uint64_t (&ek)[NSORT], int lane
     }
 }
 
-// exact fp32 score of the item at sweep position p (same fmaf chain as the fp32 kernel and the oracle)
-__device__ __forceinline__ uint64_t exact_key(const ScrArgs& a, const float* __restrict__ u, uint32_t p)
+// exact fp32 score of the item at sweep position p: the same sequential fmaf chain as the fp32 kernel and
+// the oracle (bit-exact), with the 64 floats of each block of the item row loaded up front (one memory
+// latency per block instead of one per element) and the user row read from shared memory.
+__device__ __forceinline__ uint64_t exact_key(const ScrArgs& a, const float* __restrict__ u_sm, uint32_t p)
 {
     const int item = a.perm[p];
     const float* e = a.Ei + (int64_t)item * a.lde_i;
     float s = a.bias ? a.bias[item] : 0.f;
     if (a.vec4) {
         const float4* e4 = reinterpret_cast<const float4*>(e);
-        const float4* u4 = reinterpret_cast<const float4*>(u);
-        for (int d = 0; d < a.D / 4; ++d) {
-            const float4 ev = __ldg(e4 + d);
-            const float4 uv = __ldg(u4 + d);
-            s = fmaf(uv.x, ev.x, s);
-            s = fmaf(uv.y, ev.y, s);
-            s = fmaf(uv.z, ev.z, s);
-            s = fmaf(uv.w, ev.w, s);
+        const float4* u4 = reinterpret_cast<const float4*>(u_sm);
+        for (int d0 = 0; d0 < a.D / 4; d0 += 16) {
+            float4 ev[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) ev[j] = __ldg(e4 + d0 + j);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float4 uv = u4[d0 + j];
+                s = fmaf(uv.x, ev[j].x, s);
+                s = fmaf(uv.y, ev[j].y, s);
+                s = fmaf(uv.z, ev[j].z, s);
+                s = fmaf(uv.w, ev[j].w, s);
+            }
         }
     } else {
-        for (int d = 0; d < a.D; ++d) s = fmaf(u[d], e[d], s);
+        for (int d = 0; d < a.D; ++d) s = fmaf(u_sm[d], e[d], s);
     }
     return make_key(s, item);
 }
 
 template <int NSORT>
-__device__ __forceinline__ void rescore_sort_write(const ScrArgs& a, const float* __restrict__ urow,
+__device__ __forceinline__ void rescore_sort_write(const ScrArgs& a, const float* __restrict__ u_sm,
                                                    const uint64_t* __restrict__ s_row, int cnt, int lane, int64_t rb)
 {
     uint64_t ek[NSORT];
 #pragma unroll
     for (int c = 0; c < NSORT; ++c) {
         const int j = c * 32 + lane;
-        ek[c] = (j < cnt) ? exact_key(a, urow, (uint32_t)s_row[j]) : 0ull;
+        ek[c] = (j < cnt) ? exact_key(a, u_sm, (uint32_t)s_row[j]) : 0ull;
     }
     final_sort_write<NSORT>(ek, lane, a, rb);
 }
 
+// ---- 3a. the sweep kernel (TMA + tcgen05 + screening epilogue) ----------------------------------------
+// phase 0: every 256-user group sweeps tiles [0, first_check) and stores its row state.
+// phase 1: groups whose rows still need tiles (group_need, written by the checkpoint kernel) continue from
+//          first_check with in-kernel stop checks at doubling tile counts; groups are handed out dynamically.
 template <int NPL, bool HAS_BIAS>
 __global__ void __launch_bounds__(kScrThreads, 1)
-    score_screen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, ScrArgs a)
+    score_screen_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, ScrArgs a,
+                              int phase)
 {
     constexpr int CAP = 32 * NPL;
     constexpr int TRIG = CAP - 32;
@@ -409,11 +468,12 @@ __global__ void __launch_bounds__(kScrThreads, 1)
     uint64_t* a_full = bars + 2 * kScrMaxStages + 8;
     uint64_t* a_empty = bars + 2 * kScrMaxStages + 9;
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kScrMaxStages + 10);
-    int* sm_need = reinterpret_cast<int*>(bars + 2 * kScrMaxStages + 11);  // tiles still needed by this CTA's rows
+    int* sm_need = reinterpret_cast<int*>(bars + 2 * kScrMaxStages + 11);  // [0] tiles still needed, [1] next group
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_groups = (a.B + kRowsPerCta - 1) / kRowsPerCta;
     const int n_itiles = (a.I + kSN - 1) / kSN;
+    const int T0 = a.first_check < n_itiles ? a.first_check : n_itiles;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < n_stages; ++s) {
@@ -426,7 +486,7 @@ __global__ void __launch_bounds__(kScrThreads, 1)
         }
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
-        *sm_need = 0;
+        sm_need[0] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
@@ -449,19 +509,46 @@ __global__ void __launch_bounds__(kScrThreads, 1)
     const int q = warp & 3;
     const int row_cta = u * kSM + q * 32 + lane;  // epilogue: row inside the CTA's 256 users
     const int warp_row0 = u * kSM + q * 32;
-    uint64_t* cta_slots = a.slots + (int64_t)blockIdx.x * kRowsPerCta * CAP;
     float* strip = sm_strip + (ew < 0 ? 0 : ew) * 1024;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const float bias_abs_max = (HAS_BIAS && a.biasmax_bits) ? __uint_as_float(*a.biasmax_bits) : 0.f;
-    unsigned long long st_slow = 0, st_app = 0, st_resc = 0, st_tiles = 0;
+    unsigned long long st_slow = 0, st_app = 0, st_tiles = 0;
 
-    for (int ug = blockIdx.x; ug < n_groups; ug += gridDim.x) {
+    int ug_static = blockIdx.x;
+    while (true) {
+        // ---- next group ----
+        int ug;
+        if (phase == 0) {
+            ug = ug_static;
+            ug_static += gridDim.x;
+        } else {
+            if (threadIdx.x == 0) {
+                int gi;
+                do {
+                    gi = atomicAdd(a.work_counter, 1);
+                } while (gi < n_groups && a.group_need[gi] <= T0 && a.debug != 3);
+                sm_need[1] = gi;
+            }
+            __syncthreads();
+            ug = sm_need[1];
+            __syncthreads();
+        }
+        if (ug >= n_groups) break;
+        int it = 0, it_end = T0, next_check = 0x7fffffff;
+        if (phase == 1) {
+            it = T0;
+            it_end = a.debug == 3 ? n_itiles : min(a.group_need[ug], n_itiles);
+            next_check = 2 * T0;
+            if (it >= it_end) continue;  // (debug == 3 with a one-segment catalogue)
+        }
+
         // ---- group prologue ----
         int cnt = 0, chk = 0;
         float L = INFINITY;
         RowConst rc = {0.f, 0.f, 0.f, 0.f};
         int64_t mlo = 0, mhi = 0;
-        bool force_exact = false;
+        const int64_t b = (int64_t)ug * kRowsPerCta + row_cta;
+        uint64_t* cta_slots = a.slots + (int64_t)ug * kRowsPerCta * CAP;
         if (warp == 0) {
             if (lane == 0) {
                 mbar_wait(a_empty, a_phase ^ 1);
@@ -477,22 +564,19 @@ __global__ void __launch_bounds__(kScrThreads, 1)
                 mbar_wait(a_full, a_phase);
                 a_phase ^= 1;
             }
-        } else {
-            const int64_t b = (int64_t)ug * kRowsPerCta + row_cta;
-            if (b < a.B) {
-                rc = a.row_const[b];
-                L = -INFINITY;  // running lower bound of the row's exact K-th score
-                if (a.mask_rowptr != nullptr) {
-                    mlo = a.mask_rowptr[b];
-                    mhi = a.mask_rowptr[b + 1];
-                }
-                force_exact = (int64_t)a.I - (mhi - mlo) < (int64_t)a.K;
-                if (force_exact || !(rc.na < INFINITY)) L = INFINITY;  // redone on the fp32 path: nothing to collect
+        } else if (b < a.B) {
+            rc = a.row_const[b];
+            const bool fe = row_force_exact(a, b, mlo, mhi);
+            if (phase == 0) {
+                L = (fe || !(rc.na < INFINITY)) ? INFINITY : -INFINITY;  // +inf: redone on the fp32 path, collect nothing
+            } else {
+                cnt = a.row_cnt[b];
+                chk = a.row_chk[b];
+                L = a.row_L[b];
             }
         }
 
         // ---- sweep in segments [it, seg_end); the stop tile is re-agreed at doubling checkpoints ----
-        int it = 0, it_end = n_itiles, next_check = a.first_check;
         while (it < it_end) {
             const int seg_end = it_end < next_check ? it_end : next_check;
             if (warp == 0) {
@@ -629,12 +713,12 @@ __global__ void __launch_bounds__(kScrThreads, 1)
             }
             it = seg_end;
             if (it < it_end) {
-                // ---- checkpoint: how many tiles do this CTA's rows still need? ----
+                // ---- in-kernel checkpoint (phase 1 only): how many tiles do this CTA's rows still need? ----
                 if (warp >= 2 && a.debug == 0) {
                     // tighten every live row's L first (a prune needs >= K keys to say anything)
                     for (int l = 0; l < 32; ++l) {
                         const int cnt_l = __shfl_sync(0xffffffffu, cnt, l);
-                        if (cnt_l < a.K) continue;  // warp-uniform
+                        if (cnt_l < a.K || cnt_l == __shfl_sync(0xffffffffu, chk, l)) continue;  // warp-uniform
                         const PruneResult pr = screen_prune<NPL>(
                             cta_slots + (int64_t)(warp_row0 + l) * CAP, cnt_l, __shfl_sync(0xffffffffu, chk, l),
                             __shfl_sync(0xffffffffu, rc.ce, l), __shfl_sync(0xffffffffu, rc.ab, l), a.nb, a.perm,
@@ -646,70 +730,30 @@ __global__ void __launch_bounds__(kScrThreads, 1)
                             L = fmaxf(L, pr.lbK);
                         }
                     }
-                    // smallest tile index j >= it with  |u| * nb[j * 128] (+ bias) < L : tiles [it, j) still matter
-                    int lo = it, hi = it_end;
-                    if (L == INFINITY) {
-                        hi = it;  // finished / dead / padding row
-                    } else if (L > -INFINITY) {
-                        const float bt = HAS_BIAS ? rc.sc * bias_abs_max : 0.f;
-                        while (lo < hi) {
-                            const int mid = (lo + hi) >> 1;
-                            if (fmaf(rc.na, a.nb[(int64_t)mid * kSN], bt) * 1.000001f < L)
-                                hi = mid;
-                            else
-                                lo = mid + 1;
-                        }
-                    }
-                    int need_tiles = hi;
+                    int need_tiles = tiles_needed(a, rc, L, bias_abs_max, it, it_end);
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) need_tiles = max(need_tiles, __shfl_xor_sync(0xffffffffu, need_tiles, o));
-                    if (lane == 0) atomicMax(sm_need, need_tiles);
+                    if (lane == 0) atomicMax(&sm_need[0], need_tiles);
                 } else if (warp >= 2 && lane == 0) {
-                    atomicMax(sm_need, it_end);
+                    atomicMax(&sm_need[0], it_end);
                 }
                 __syncthreads();
-                const int agreed = *sm_need;
+                const int agreed = sm_need[0];
                 __syncthreads();
-                if (threadIdx.x == 0) *sm_need = 0;
+                if (threadIdx.x == 0) sm_need[0] = 0;
                 if (agreed < it_end) it_end = agreed > it ? agreed : it;
                 if (a.debug == 3) it_end = n_itiles;
                 next_check = next_check * 2;
             }
         }
 
-        // ---- group epilogue ----
+        // ---- group epilogue: hand the row state to the next kernel ----
         if (warp == 1) {
             if (lane == 0) tc_commit(a_empty);  // A' tiles free once every MMA of this group retired
-        } else if (warp >= 2 && (a.debug == 0 || a.debug == 3)) {
-            // prune, exact re-score, sort, write (the warp walks its 32 rows)
-            for (int l = 0; l < 32; ++l) {
-                const int64_t rb = (int64_t)ug * kRowsPerCta + warp_row0 + l;
-                if (rb >= a.B) break;  // rows are contiguous: warp-uniform exit
-                int cnt_l = __shfl_sync(0xffffffffu, cnt, l);
-                bool fallback = __shfl_sync(0xffffffffu, (int)force_exact, l) != 0 || cnt_l < a.K;
-                uint64_t* s_row = cta_slots + (int64_t)(warp_row0 + l) * CAP;
-                if (!fallback) {
-                    const PruneResult pr = screen_prune<NPL>(
-                        s_row, cnt_l, __shfl_sync(0xffffffffu, chk, l), __shfl_sync(0xffffffffu, rc.ce, l),
-                        __shfl_sync(0xffffffffu, rc.ab, l), a.nb, a.perm, a.mask_items, __shfl_sync(0xffffffffu, mlo, l),
-                        __shfl_sync(0xffffffffu, mhi, l), a.K, lane, a.stats);
-                    cnt_l = pr.cnt;
-                    fallback = cnt_l < a.K;  // overflow (-1) or too few unmasked candidates
-                }
-                if (!fallback) {
-                    const float* urow = a.Eu + (a.users ? a.users[rb] : rb) * a.lde_u;
-                    st_resc += cnt_l;
-                    if (cnt_l <= 64)
-                        rescore_sort_write<2>(a, urow, s_row, cnt_l, lane, rb);
-                    else if (cnt_l <= 128)
-                        rescore_sort_write<4>(a, urow, s_row, cnt_l, lane, rb);
-                    else
-                        rescore_sort_write<NPL>(a, urow, s_row, cnt_l, lane, rb);
-                } else if (lane == 0) {
-                    a.fallback_rows[atomicAdd(a.fallback_count, 1)] = (int32_t)rb;
-                }
-            }
-            __syncwarp();
+        } else if (warp >= 2 && b < a.B) {
+            a.row_cnt[b] = cnt;
+            a.row_chk[b] = chk;
+            a.row_L[b] = L;
         }
     }
     if (warp >= 2 && a.stats != nullptr) {
@@ -718,7 +762,6 @@ __global__ void __launch_bounds__(kScrThreads, 1)
         if (lane == 0) {
             atomicAdd(&a.stats[0], st_slow);
             atomicAdd(&a.stats[1], st_app / 32);  // every lane counted each append
-            atomicAdd(&a.stats[5], st_resc);
             if (ew == 0) atomicAdd(&a.stats[6], st_tiles);  // item tiles swept, summed over user groups
         }
     }
@@ -728,6 +771,83 @@ __global__ void __launch_bounds__(kScrThreads, 1)
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
+}
+
+// ---- 3b. checkpoint after phase 0: one warp per row at full occupancy --------------------------------
+// Applies the train-history mask to the row's first candidates, computes L and the number of item tiles the
+// row still needs; the maximum over each 256-user group decides whether phase 1 touches the group at all.
+template <int NPL>
+__global__ void __launch_bounds__(256)
+    score_screen_checkpoint_kernel(ScrArgs a)
+{
+    constexpr int CAP = 32 * NPL;
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= a.B) return;
+    const int n_itiles = (a.I + kSN - 1) / kSN;
+    const int T0 = a.first_check < n_itiles ? a.first_check : n_itiles;
+    const RowConst rc = a.row_const[b];
+    int64_t mlo, mhi;
+    row_force_exact(a, b, mlo, mhi);
+    int cnt = a.row_cnt[b];
+    float L = a.row_L[b];
+    if (cnt >= a.K) {
+        const PruneResult pr = screen_prune<NPL>(a.slots + b * CAP, cnt, a.row_chk[b], rc.ce, rc.ab, a.nb, a.perm,
+                                                 a.mask_items, mlo, mhi, a.K, lane, a.stats);
+        cnt = pr.cnt;
+        L = fmaxf(L, pr.lbK);
+        if (lane == 0) {
+            a.row_cnt[b] = cnt;
+            a.row_chk[b] = cnt;
+            a.row_L[b] = L;
+        }
+    }
+    if (lane == 0) {
+        const float bias_abs_max = a.biasmax_bits ? __uint_as_float(*a.biasmax_bits) : 0.f;
+        const int need = tiles_needed(a, rc, L, bias_abs_max, T0, n_itiles);
+        if (need > T0) atomicMax(&a.group_need[b / kRowsPerCta], need);
+    }
+}
+
+// ---- 3c. finalisation: one warp per row at full occupancy ---------------------------------------------
+// Last prune if anything was appended since the previous one, exact fp32 re-score of the survivors, sort by
+// (score desc, id asc), write the top K; undecidable rows are queued for the fp32 kernel.
+template <int NPL>
+__global__ void __launch_bounds__(256)
+    score_screen_finalize_kernel(ScrArgs a)
+{
+    constexpr int CAP = 32 * NPL;
+    __shared__ __align__(16) float u_sm[8][256];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + w;
+    if (b >= a.B) return;
+    const RowConst rc = a.row_const[b];
+    int64_t mlo, mhi;
+    const bool fe = row_force_exact(a, b, mlo, mhi);
+    int cnt = a.row_cnt[b];
+    const int chk = a.row_chk[b];
+    uint64_t* s_row = a.slots + b * CAP;
+    bool fallback = fe || cnt < a.K;
+    if (!fallback && cnt != chk) {  // appended since the last prune
+        const PruneResult pr = screen_prune<NPL>(s_row, cnt, chk, rc.ce, rc.ab, a.nb, a.perm, a.mask_items, mlo, mhi, a.K, lane,
+                                                 a.stats);
+        cnt = pr.cnt;
+        fallback = cnt < a.K;  // overflow (-1) or too few unmasked candidates
+    }
+    if (fallback) {
+        if (lane == 0) a.fallback_rows[atomicAdd(a.fallback_count, 1)] = (int32_t)b;
+        return;
+    }
+    const float* urow = a.Eu + (a.users ? a.users[b] : b) * a.lde_u;
+    for (int d = lane; d < a.D; d += 32) u_sm[w][d] = urow[d];
+    __syncwarp();
+    if (a.stats && lane == 0) atomicAdd(&a.stats[5], (unsigned long long)cnt);
+    if (cnt <= 64)
+        rescore_sort_write<2>(a, u_sm[w], s_row, cnt, lane, b);
+    else if (cnt <= 128)
+        rescore_sort_write<4>(a, u_sm[w], s_row, cnt, lane, b);
+    else
+        rescore_sort_write<NPL>(a, u_sm[w], s_row, cnt, lane, b);
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -796,7 +916,8 @@ static size_t scr_sort_temp_bytes(int32_t I)
 }
 
 struct ScrLayout {
-    int64_t a_h, b_h, row_const, nb, perm, nb_raw, ident, sort_tmp, misc, fallback, slots, simt, total;
+    int64_t a_h, b_h, row_const, nb, perm, nb_raw, ident, sort_tmp, misc, fallback, row_cnt, row_chk, row_L, group_need,
+        slots, simt, total;
     int64_t sort_tmp_bytes;
     int32_t b_pad, i_pad;
 };
@@ -822,9 +943,13 @@ static ScrLayout scr_layout(int32_t B, int32_t I, int32_t D, int32_t K)
     L.ident = take((int64_t)L.i_pad * 4);
     L.sort_tmp_bytes = (int64_t)scr_sort_temp_bytes(I);
     L.sort_tmp = take(L.sort_tmp_bytes);
-    L.misc = take(256);  // u32 [0] item absmax bits, [1] fallback count, [3] bias absmax; u64 stats at +64
+    L.misc = take(256);  // u32 [0] item absmax bits, [1] fallback count, [3] bias absmax, [4] group scheduler; u64 stats at +64
     L.fallback = take((int64_t)B * 4);
-    L.slots = take((int64_t)scr_grid(B) * kRowsPerCta * cap * 8);
+    L.row_cnt = take((int64_t)L.b_pad * 4);
+    L.row_chk = take((int64_t)L.b_pad * 4);
+    L.row_L = take((int64_t)L.b_pad * 4);
+    L.group_need = take((int64_t)(L.b_pad / kRowsPerCta) * 4);
+    L.slots = take((int64_t)L.b_pad * cap * 8);
     L.simt = take(score_simt_workspace_bytes(B, K));
     L.total = off;
     return L;
@@ -919,33 +1044,45 @@ int score_topk_screen_launch(const float* Eu, int64_t lde_u, const int64_t* user
     a.mask_rowptr = mask_rowptr; a.mask_items = mask_items; a.K = K; a.out_ids = out_ids; a.out_scores = out_scores;
     a.slots = (uint64_t*)(ws + L.slots); a.row_const = row_const; a.nb = nb; a.perm = perm;
     a.biasmax_bits = bias ? misc + 3 : nullptr;
+    a.row_cnt = (int32_t*)(ws + L.row_cnt); a.row_chk = (int32_t*)(ws + L.row_chk); a.row_L = (float*)(ws + L.row_L);
+    a.group_need = (int32_t*)(ws + L.group_need); a.work_counter = (int32_t*)(misc + 4);
     a.fallback_rows = fallback; a.fallback_count = (int32_t*)(misc + 1); a.n_stages = n_stages;
     a.vec4 = ((lde_u % 4 == 0) && (lde_i % 4 == 0) && ((uintptr_t)Eu % 16 == 0) && ((uintptr_t)Ei % 16 == 0)) ? 1 : 0;
     a.first_check = (2 * K + kSN - 1) / kSN;  // enough tiles for ~2K candidates before the first stop check
     a.stats = getenv("GMR_SCREEN_STATS") ? (unsigned long long*)(ws + L.misc + 64) : nullptr;
     a.debug = getenv("GMR_TC_DEBUG") ? atoi(getenv("GMR_TC_DEBUG")) : 0;
+    const int n_groups = L.b_pad / kRowsPerCta;
+    GMR_CHECK_CUDA(cudaMemsetAsync(a.group_need, 0, (size_t)n_groups * 4, st));
     const int grid = scr_grid(B);
     const int npl = scr_npl(K);
-#define GMR_SCR_LAUNCH(NPL)                                                                                        \
+    const int row_blocks = (B + 7) / 8;
+    // phase 0 sweep -> checkpoint (mask + first L, per row at full occupancy) -> phase 1 sweep for the groups that
+    // still need tiles -> finalisation (exact re-score + sort, per row at full occupancy)
+#define GMR_SCR_LAUNCH(NPL, BIAS)                                                                                  \
     do {                                                                                                           \
-        if (bias != nullptr) {                                                                                     \
-            GMR_CHECK_CUDA(cudaFuncSetAttribute(score_screen_kernel<NPL, true>,                                    \
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
-            score_screen_kernel<NPL, true><<<grid, kScrThreads, smem, st>>>(map_a, map_b, a);                      \
-        } else {                                                                                                   \
-            GMR_CHECK_CUDA(cudaFuncSetAttribute(score_screen_kernel<NPL, false>,                                   \
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
-            score_screen_kernel<NPL, false><<<grid, kScrThreads, smem, st>>>(map_a, map_b, a);                     \
+        GMR_CHECK_CUDA(cudaFuncSetAttribute(score_screen_sweep_kernel<NPL, BIAS>,                                  \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+        score_screen_sweep_kernel<NPL, BIAS><<<grid, kScrThreads, smem, st>>>(map_a, map_b, a, 0);                 \
+        GMR_LAUNCH_CHECK();                                                                                        \
+        if (a.debug == 0 || a.debug == 3) {                                                                        \
+            score_screen_checkpoint_kernel<NPL><<<row_blocks, 256, 0, st>>>(a);                                    \
+            GMR_LAUNCH_CHECK();                                                                                    \
+        }                                                                                                          \
+        score_screen_sweep_kernel<NPL, BIAS><<<grid, kScrThreads, smem, st>>>(map_a, map_b, a, 1);                 \
+        GMR_LAUNCH_CHECK();                                                                                        \
+        if (a.debug == 0 || a.debug == 3) {                                                                        \
+            score_screen_finalize_kernel<NPL><<<row_blocks, 256, 0, st>>>(a);                                      \
+            GMR_LAUNCH_CHECK();                                                                                    \
         }                                                                                                          \
     } while (0)
-    if (npl == 8)
-        GMR_SCR_LAUNCH(8);
-    else if (npl == 16)
-        GMR_SCR_LAUNCH(16);
-    else
-        GMR_SCR_LAUNCH(32);
+    if (npl == 8) {
+        if (bias) GMR_SCR_LAUNCH(8, true); else GMR_SCR_LAUNCH(8, false);
+    } else if (npl == 16) {
+        if (bias) GMR_SCR_LAUNCH(16, true); else GMR_SCR_LAUNCH(16, false);
+    } else {
+        if (bias) GMR_SCR_LAUNCH(32, true); else GMR_SCR_LAUNCH(32, false);
+    }
 #undef GMR_SCR_LAUNCH
-    GMR_LAUNCH_CHECK();
     // queued rows: exact fp32 kernel, row count read on the device (no host synchronisation)
     score_simt_set_dynamic_rows((const int32_t*)(misc + 1));
     const int fb_grid = 2 * sm_count() < (B + 127) / 128 ? 2 * sm_count() : (B + 127) / 128;

@@ -391,6 +391,51 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// out[:, 0:D] = w1 * n(act(x1)) + w2 * n(act(x2)),  out[:, D:2D] = out[:, 0:D] + y   (y optional)
+// with act = leaky ReLU (slope) and n(v) = v / max(||v||_2, eps); one warp per row, values kept in
+// registers between the norm pass and the write (D <= 256).
+__global__ void __launch_bounds__(256)
+    rows_normalize_mix_kernel(const float* __restrict__ x1, int64_t ld1, const float* __restrict__ x2, int64_t ld2,
+                              const float* __restrict__ y, int64_t ldy, float* __restrict__ out, int64_t ldo,
+                              int64_t n_rows, int32_t D, float w1, float w2, float slope, float eps)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n_rows) return;
+    float a[8], b[8];
+    float sa = 0.f, sb = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int d = lane + 32 * j;
+        a[j] = b[j] = 0.f;
+        if (d < D) {
+            float v = x1[r * ld1 + d];
+            v = v > 0.f ? v : v * slope;
+            a[j] = v;
+            sa = fmaf(v, v, sa);
+            v = x2[r * ld2 + d];
+            v = v > 0.f ? v : v * slope;
+            b[j] = v;
+            sb = fmaf(v, v, sb);
+        }
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        sa += __shfl_xor_sync(0xffffffffu, sa, m);
+        sb += __shfl_xor_sync(0xffffffffu, sb, m);
+    }
+    const float ia = w1 / fmaxf(sqrtf(sa), eps), ib = w2 / fmaxf(sqrtf(sb), eps);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int d = lane + 32 * j;
+        if (d < D) {
+            const float z = fmaf(ia, a[j], ib * b[j]);
+            out[r * ldo + d] = z;
+            if (y != nullptr) out[r * ldo + D + d] = z + y[r * ldy + d];
+        }
+    }
+}
+
 }  // namespace gmr
 
 // ---- C ABI -------------------------------------------------------------------------------------
@@ -533,6 +578,21 @@ extern "C" int gmr_rows_axpby_norm_f32(const float* x, int64_t ldx, const float*
     const int wpb = 8;
     gmr::rows_axpby_norm_kernel<<<(unsigned)((n_rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
         x, ldx, y, ldy, z, ldz, out, ldo, n_rows, D, a, b, c, eps);
+    GMR_LAUNCH_CHECK();
+    return GMR_OK;
+}
+
+extern "C" int gmr_rows_normalize_mix_f32(const float* x1, int64_t ld1, const float* x2, int64_t ld2, const float* y,
+                                          int64_t ldy, float* out, int64_t ldo, int64_t n_rows, int32_t D, float w1,
+                                          float w2, float slope, float eps, void* stream)
+{
+    GMR_REQUIRE(x1 != nullptr && x2 != nullptr && out != nullptr, "gmr_rows_normalize_mix_f32: null x1/x2/out");
+    GMR_REQUIRE(D >= 1 && D <= 256 && n_rows >= 0, "gmr_rows_normalize_mix_f32: D must be in [1, 256] (got %d)", D);
+    GMR_REQUIRE(ldo >= (y ? 2 * D : D), "gmr_rows_normalize_mix_f32: ldo too small");
+    if (n_rows == 0) return GMR_OK;
+    const int wpb = 8;
+    gmr::rows_normalize_mix_kernel<<<(unsigned)((n_rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+        x1, ld1, x2, ld2, y, ldy, out, ldo, n_rows, D, w1, w2, slope, eps);
     GMR_LAUNCH_CHECK();
     return GMR_OK;
 }

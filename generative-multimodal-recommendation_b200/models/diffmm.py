@@ -2,16 +2,12 @@
 
 Hot path (diffmm.py:129-169, ``forward_MM``): 6 + n_layers ``torch.spmm`` calls over the normalised
 user-item adjacency ``A`` and the two diffusion-generated modality graphs, then
-``matmul(usr[user], itm.T)`` (:276-278).  Under ``no_grad`` the propagation is restructured around the
-bipartite blocks of ``A``:
-
-    [H_v | H_t | G ]_users = R_hat  . [F_v | F_t | I0]      one 192-wide pass over the user rows
-    [G_v | G_t | H ]_items = R_hat' . [H_v | H_t | U0]      one 192-wide pass over the item rows
-
-which yields every H_m / G_m block of the reference's four 64-wide full-matrix SpMMs (two of whose
-halves it computes twice) with bit-identical rows, in 2 kernel launches that read the CSR once per
-half.  With autograd enabled (training) the literal sequence of the reference is used, through the
-differentiable ``ops.spmm``.
+``matmul(usr[user], itm.T)`` (:276-278).  Under ``no_grad`` the propagation is regrouped around the
+bipartite blocks of ``A`` and by linearity of the modality mix
+(``_forward_mm_fused``): one 128-wide pass over the user rows, one 64-wide pass over the item rows, the
+two modality-graph products accumulated in place, then the ``n_layers`` full-graph passes -- against the
+reference's four 64-wide full-matrix SpMMs (two of whose halves it computes twice).  With autograd
+enabled (training) the literal sequence of the reference is used, through the differentiable ``ops.spmm``.
 
 Out of scope here: the diffusion / denoise networks and their trainer.  The
 modality graphs are attributes the caller sets (``image_UI_matrix`` / ``text_UI_matrix``), exactly as
@@ -24,7 +20,7 @@ import torch.nn.functional as F
 
 from ..common.abstract_recommender import GeneralRecommender
 from .. import graph as gb
-from ..ops import GraphCSR, spmm, spmm_raw
+from ..ops import GraphCSR, rows_axpby_norm, rows_normalize_mix, spmm, spmm_raw
 from ._common import BipartiteAdj, as_graph
 
 init = nn.init.xavier_uniform_
@@ -121,34 +117,66 @@ class DiffMM(GeneralRecommender):
             return self._forward_mm_fused(adj, as_graph(image_adj), as_graph(text_adj))
         return self._forward_mm_literal(as_graph(adj), as_graph(image_adj), as_graph(text_adj))
 
-    def _forward_mm_fused(self, adj, image_adj, text_adj):
+    def _modal_weights_host(self):
+        """softmax(modal_weight) as two Python floats, re-read from the device only when the parameter changed."""
+        sig = (id(self.modal_weight), self.modal_weight._version)
+        if self.__dict__.get("_mw_sig") != sig:
+            w = self.softmax(self.modal_weight.detach()).tolist()
+            self.__dict__["_mw_sig"], self.__dict__["_mw_val"] = sig, (float(w[0]), float(w[1]))
+        return self.__dict__["_mw_val"]
+
+    def _packed_e0(self):
+        """[U0; I0] as ONE [N, d] buffer without a per-step concat: the two embedding tables are re-homed (once)
+        as the two row blocks of a single allocation; the parameters keep their identity and values."""
         nu, d = self.n_users, self.latdim
-        u0, i0 = self.uEmbeds.detach(), self.iEmbeds.detach()
-        weight = self.softmax(self.modal_weight)
-        xi = torch.empty((self.n_items, 3 * d), dtype=torch.float32, device=self.device)
-        xi[:, 0:d] = F.normalize(self.getImageFeats())
-        xi[:, d:2 * d] = F.normalize(self.getTextFeats())
-        xi[:, 2 * d:] = i0
-        yu = spmm_raw(adj.ui, xi)                       # [U, 3d] = H_v | H_t | G   (user rows)
-        xu = torch.cat([yu[:, :2 * d], u0], dim=1)      # [U, 3d] = H_v | H_t | U0
-        yi = spmm_raw(adj.iu, xu)                       # [I, 3d] = G_v | G_t | H   (item rows)
-        e0 = torch.cat([u0, i0])
-        p_img = spmm_raw(image_adj, e0)
-        p_txt = spmm_raw(text_adj, e0)
+        u, i = self.uEmbeds, self.iEmbeds
+        buf = self.__dict__.get("_e0_buf")
+        if (buf is None or buf.device != u.device or u.data_ptr() != buf.data_ptr()
+                or i.data_ptr() != buf.data_ptr() + nu * d * 4):
+            buf = torch.cat([u.detach(), i.detach()])
+            u.data = buf[:nu]
+            i.data = buf[nu:]
+            self.__dict__["_e0_buf"] = buf
+        return buf
 
-        def combine(h_u, g_u, g_i, h_i, p):
-            e = torch.cat([h_u + g_u, h_i + g_i])
-            return e + self.ris_adj_lambda * p
+    def _forward_mm_fused(self, adj, image_adj, text_adj):
+        """forward_MM regrouped by linearity (same real-arithmetic result, fp32 rounding differs at the 1e-7
+        level, well inside the 1e-5 parity bound):
 
-        e_img = combine(yu[:, 0:d], yu[:, 2 * d:], yi[:, 0:d], yi[:, 2 * d:], p_img)
-        e_txt = combine(yu[:, d:2 * d], yu[:, 2 * d:], yi[:, d:2 * d], yi[:, 2 * d:], p_txt)
-        modal = weight[0] * e_img + weight[1] * e_txt
-        embeds = modal
-        last = modal
-        for _ in range(self.gnn_layer):
+            Z       = w0 n(F_v) + w1 n(F_t)                      (w0 + w1 = 1: softmax)
+            modal_u = w0 (H_v + G_v)_u + w1 (H_t + G_t)_u = R_hat (Z + I0)
+            modal_i = w0 (H_v + G_v)_i + w1 (H_t + G_t)_i = R_hat' (U0 + R_hat Z)
+            modal  += ris_adj_lambda (w0 A_v + w1 A_t) [U0; I0]
+
+        i.e. one 128-wide pass over the user rows ([R_hat Z | R_hat (Z + I0)]), one 64-wide pass over the item
+        rows and the two modality-graph products accumulated in place, instead of two 192-wide passes."""
+        nu, ni, d = self.n_users, self.n_items, self.latdim
+        n = nu + ni
+        w0, w1 = self._modal_weights_host()
+        e0 = self._packed_e0()
+        u0, i0 = e0[:nu], e0[nu:]
+        pv = torch.mm(self.v_feat, self.image_trans.detach())
+        pt = torch.mm(self.t_feat, self.text_trans.detach())
+        xi = rows_normalize_mix(pv, pt, w0, w1, y=i0, slope=self.leakyrelu.negative_slope)   # [I, 2d] = Z | Z + I0
+        # work[:, d:] is `modal` (row pitch 2d); work[:nu, :d] receives R_hat Z
+        work = torch.empty((n, 2 * d), dtype=torch.float32, device=self.device)
+        spmm_raw(adj.ui, xi, out=work[:nu])                           # users: [R_hat Z | modal_u]
+        xu = torch.add(u0, work[:nu, :d])                             # U0 + R_hat Z
+        modal = work[:, d:]
+        spmm_raw(adj.iu, xu, out=modal[nu:])                          # items: modal_i
+        spmm_raw(image_adj, e0, out=modal, alpha=self.ris_adj_lambda * w0, beta=1.0)
+        spmm_raw(text_adj, e0, out=modal, alpha=self.ris_adj_lambda * w1, beta=1.0)
+        if self.gnn_layer == 0:
+            embeds = rows_axpby_norm(modal, None, modal, a=1.0, c=self.ris_lambda)
+            return embeds[:nu], embeds[nu:]
+        last = spmm_raw(adj.full, modal)
+        if self.gnn_layer == 1:
+            embeds = rows_axpby_norm(modal, last, modal, a=1.0, b=1.0, c=self.ris_lambda)   # modal + L1 + lambda n(modal)
+            return embeds[:nu], embeds[nu:]
+        embeds = rows_axpby_norm(modal, last, modal, a=1.0, b=1.0, c=self.ris_lambda)
+        for _ in range(self.gnn_layer - 1):
             last = spmm_raw(adj.full, last)
-            embeds = embeds + last
-        embeds = embeds + self.ris_lambda * F.normalize(modal)
+            embeds = rows_axpby_norm(embeds, last, None, a=1.0, b=1.0, out=embeds)
         return embeds[:nu], embeds[nu:]
 
     def _forward_mm_literal(self, adj, image_adj, text_adj):

@@ -238,6 +238,28 @@ def rows_axpby_norm(x, y=None, z=None, a=1.0, b=0.0, c=0.0, eps=1e-12, out=None)
     return out
 
 
+def rows_normalize_mix(x1, x2, w1, w2, y=None, slope=1.0, eps=1e-12, out=None):
+    """out[:, :D] = w1 * normalize(lrelu(x1)) + w2 * normalize(lrelu(x2)); with ``y``, out[:, D:2D] = out[:, :D] + y
+    (modality mix of diffmm.py:131-145 in one pass)."""
+    global LAUNCHES
+    lib = _lib.load()
+    n, d = int(x1.shape[0]), int(x1.shape[1])
+    width = 2 * d if y is not None else d
+    if out is None:
+        out = torch.empty((n, width), dtype=torch.float32, device=x1.device)
+    p1, ld1 = _rows(x1, "x1")
+    p2, ld2 = _rows(x2, "x2")
+    py, ldy = _rows(y, "y") if y is not None else (C.c_void_p(0), 0)
+    po, ldo = _rows(out, "out")
+    if out.shape[0] != n or out.shape[1] < width:
+        raise ValueError("rows_normalize_mix: out has shape %s, need [%d, >= %d]" % (tuple(out.shape), n, width))
+    with torch.cuda.device(x1.device):
+        _lib.check(lib.gmr_rows_normalize_mix_f32(p1, ld1, p2, ld2, py, ldy, po, ldo, n, d, float(w1), float(w2),
+                                                  float(slope), float(eps), _stream()), "gmr_rows_normalize_mix_f32")
+    LAUNCHES += 1
+    return out
+
+
 def tc_supported(d, k, precision="tc"):
     """Shapes the tcgen05 scoring paths accept (operand tiles + ring stages must fit in shared memory)."""
     if precision == "tc_split":

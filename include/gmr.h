@@ -163,6 +163,15 @@ int gmr_rows_axpby_norm_f32(const float* x, int64_t ldx, const float* y, int64_t
                             float* out, int64_t ldo, int64_t n_rows, int32_t D, float a, float b, float c,
                             float eps, void* stream);
 
+/* Modality mix of the propagation step (GenMMRec/src/models/diffmm.py:131-133,138,145: leaky-ReLU'd
+ * projections, F.normalize, softmax-weighted sum) in one pass:
+ *   out[r, 0:D]  = w1 * n(act(x1[r])) + w2 * n(act(x2[r])),   n(v) = v / max(||v||_2, eps),
+ *   out[r, D:2D] = out[r, 0:D] + y[r]                         (only when y != NULL; then ldo >= 2 D)
+ * act = leaky ReLU with negative slope `slope` (1.0 = identity).  D <= 256. */
+int gmr_rows_normalize_mix_f32(const float* x1, int64_t ld1, const float* x2, int64_t ld2, const float* y, int64_t ldy,
+                               float* out, int64_t ldo, int64_t n_rows, int32_t D, float w1, float w2, float slope,
+                               float eps, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Peer-memory plumbing for the fused SpMM + all-gather (CUDA IPC, one process per GPU).
  * gmr_peer_alloc allocates `bytes` of device memory suitable for export; gmr_peer_export fills a
