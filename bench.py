@@ -44,6 +44,16 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of our kernels, from the committed ncu --set full
+    captures (profiles/ncu_traffic.json: kernel key -> bytes); absent keys report null."""
+    path = os.path.join(REPO, "profiles", "ncu_traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return {}
+
+
 class ClockSampler(object):
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
 
@@ -248,6 +258,12 @@ def run_gpu(args):
     ms_total, wall, launches, prof = timed(step_resident, args.steps, args.warmup, profile=True)
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, _, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    if os.environ.get("GMR_PROFILE_STEP"):  # ncu --profile-from-start off: exactly one resident step is captured
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
     result_dict, raw = trainer.evaluator.finalize(step_resident(), n_eval_total)
 
     # ---- per-kernel durations from the CUDA events recorded inside the timed region ----------------
@@ -265,27 +281,48 @@ def run_gpu(args):
             kk["gather_GBs"] = e["meta"]["nnz"] * (8 + 4 * e["meta"]["d"]) / avg / 1e6
         if e["op"] == "score_topk":
             kk["alg_TFLOPs"] = e["meta"]["flops"] / avg / 1e9
+        if e["op"] == "dense_projections":
+            kk["library"] = "torch.mm (cuBLAS fp32)"
+            kk["TFLOPs"] = e["meta"]["flops"] / avg / 1e9
+            kk["GBs"] = e["meta"]["bytes"] / avg / 1e6
         kernels[key] = kk
     step_ms = ms_total / args.steps
-    score_key = "score_topk"
-    score_share = kernels[score_key]["avg_ms"] * kernels[score_key]["launches_per_step"] / step_ms
+    for kk in kernels.values():
+        kk["share_of_step"] = kk["avg_ms"] * kk["launches_per_step"] / step_ms
     spmm_keys = [kname for kname, e in per.items() if e["op"] == "spmm"]
     big_spmm = max(spmm_keys, key=lambda kname: per[kname]["meta"]["alg_bytes"])
     prop_ms = step_ms - sum(kernels[kname]["avg_ms"] * kernels[kname]["launches_per_step"]
                             for kname in kernels if per[kname]["op"] in ("score_topk", "hits_metrics"))
-    tensor_peak = peaks["bf16_tflops_sustained"]
-    roofline = {"kernel": "score_mask_topk (%s)" % args.precision, "bound": "tensor",
-                "achieved": kernels[score_key]["alg_TFLOPs"], "peak": tensor_peak, "unit": "TFLOP/s",
-                "frac": kernels[score_key]["alg_TFLOPs"] / tensor_peak, "traffic": None,
+    traffic = load_traffic()
+
+    def hbm_roofline(kname):
+        kk = kernels[kname]
+        return {"kernel": kname, "bound": "hbm", "achieved": kk["alg_GBs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": kk["alg_GBs"] / peaks["hbm_gbs"], "traffic": traffic.get(kname),
+                "gather_model_GBs": kk["gather_GBs"], "avg_ms": kk["avg_ms"], "share_of_step": kk["share_of_step"],
+                "algorithmic_bytes_per_launch": per[kname]["meta"]["alg_bytes"],
+                "peak_source": peaks["source"] + " copy bandwidth",
+                "note": "algorithmic bytes = CSR read once + X read once + Y written once (SURVEY.md 8d); gather_model_GBs "
+                        "counts every gathered embedding row (what the L2 actually serves)"}
+
+    def tensor_roofline():
+        kk = kernels["score_topk"]
+        return {"kernel": "score_mask_topk (%s)" % args.precision, "bound": "tensor", "achieved": kk["alg_TFLOPs"],
+                "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": kk["alg_TFLOPs"] / peaks["bf16_tflops_sustained"],
+                "traffic": traffic.get("score_topk"), "avg_ms": kk["avg_ms"], "share_of_step": kk["share_of_step"],
                 "peak_source": peaks["source"] + " bf16 sustained (kernel timed inside a long step)",
-                "share_of_step": score_share,
-                "note": "algorithmic flops 2*U*I*D of the reference's dense matmul (the tc mode sweeps items in descending-norm order "
-                        "and stops when no remaining item can reach any top-K list, so it may execute far fewer; tc_split issues 3x "
-                        "product; fp32 mode runs the exact fmaf chain on CUDA cores)"}
-    roofline_spmm = {"kernel": big_spmm, "bound": "hbm", "achieved": kernels[big_spmm]["alg_GBs"],
-                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": kernels[big_spmm]["alg_GBs"] / peaks["hbm_gbs"],
-                     "traffic": None, "gather_model_GBs": kernels[big_spmm]["gather_GBs"],
-                     "peak_source": peaks["source"] + " copy bandwidth"}
+                "note": "flops = 2*U*I*D of the reference's dense matmul.  The tc mode sweeps items in descending-norm order "
+                        "and stops a 256-user group as soon as Cauchy-Schwarz rules out every remaining item, so it executes "
+                        "only the tiles that can matter: on popularity-skewed embeddings `achieved` exceeds the tensor peak "
+                        "because most of the dense product is provably irrelevant and never computed (exact results; "
+                        "GMR_TC_DEBUG=3 forces the full sweep).  tc_split issues 3x the flops; fp32 runs on CUDA cores."}
+
+    # `roofline` describes the kernel of OURS that holds the largest share of the step
+    own = [kname for kname in kernels if per[kname]["op"] in ("spmm", "score_topk")]
+    dominant = max(own, key=lambda kname: kernels[kname]["share_of_step"])
+    roofline = tensor_roofline() if per[dominant]["op"] == "score_topk" else hbm_roofline(dominant)
+    roofline_spmm = hbm_roofline(big_spmm)
+    roofline_score = tensor_roofline()
 
     out = None
     if rank == 0:
@@ -302,7 +339,7 @@ def run_gpu(args):
                        "l2": ("L2 flushed between timed steps (operands fit the %d MB L2)" % (l2_bytes >> 20)) if need_flush
                        else ("operands (%.0f MB per SpMM) exceed the %d MB L2; no flush" % (operand_bytes / 1e6, l2_bytes >> 20))},
             "propagation_step_ms": prop_ms, "spmm_hbm_GBs": kernels[big_spmm]["alg_GBs"],
-            "roofline": roofline, "roofline_spmm": roofline_spmm, "kernels": kernels,
+            "roofline": roofline, "roofline_spmm": roofline_spmm, "roofline_score": roofline_score, "kernels": kernels,
             "e2e": {"value": n_eval_total / (ms_e2e / args.steps) * 1e3, "unit": "users/s",
                     "h2d_bytes_per_step": host_in.bytes * world, "d2h_bytes_per_step": int(sums_host.numel() * 8),
                     "ms_per_step": ms_e2e / args.steps},

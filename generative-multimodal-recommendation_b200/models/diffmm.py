@@ -20,6 +20,7 @@ import torch.nn.functional as F
 
 from ..common.abstract_recommender import GeneralRecommender
 from .. import graph as gb
+from .. import ops
 from ..ops import GraphCSR, rows_axpby_norm, rows_normalize_mix, spmm, spmm_raw
 from ._common import BipartiteAdj, as_graph
 
@@ -155,8 +156,11 @@ class DiffMM(GeneralRecommender):
         w0, w1 = self._modal_weights_host()
         e0 = self._packed_e0()
         u0, i0 = e0[:nu], e0[nu:]
-        pv = torch.mm(self.v_feat, self.image_trans.detach())
+        ev = ops._prof_begin()
+        pv = torch.mm(self.v_feat, self.image_trans.detach())     # dense projections: library GEMMs
         pt = torch.mm(self.t_feat, self.text_trans.detach())
+        ops._prof_end("dense_projections", ev, flops=2.0 * ni * d * (self.image_feat_dim + self.text_feat_dim),
+                      bytes=4.0 * ni * (self.image_feat_dim + self.text_feat_dim + 2 * d))
         xi = rows_normalize_mix(pv, pt, w0, w1, y=i0, slope=self.leakyrelu.negative_slope)   # [I, 2d] = Z | Z + I0
         # work[:, d:] is `modal` (row pitch 2d); work[:nu, :d] receives R_hat Z
         work = torch.empty((n, 2 * d), dtype=torch.float32, device=self.device)

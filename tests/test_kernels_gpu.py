@@ -379,3 +379,67 @@ def test_score_tc_wide_dynamic_range(ops, precision):
 def test_score_tc_unsupported_shapes_are_loud(ops):
     with pytest.raises(RuntimeError):
         ops.score_mask_topk(torch.zeros((4, 60), device="cuda"), torch.zeros((90, 60), device="cuda"), 5, precision="tc")
+
+
+# ---- row glue + size-independent properties at larger sizes --------------------------------------------
+
+
+def test_rows_normalize_mix(ops):
+    rng = np.random.default_rng(21)
+    n, d = 777, 64
+    x1, x2, y = (torch.from_numpy(rng.standard_normal((n, d)).astype(np.float32)).cuda() for _ in range(3))
+    x1[5] = 0.0                                    # zero row: F.normalize clamps the norm at eps
+    out = ops.rows_normalize_mix(x1, x2, 0.3, 0.7, y=y, slope=0.2)
+    lr = torch.nn.functional.leaky_relu
+    z = 0.3 * torch.nn.functional.normalize(lr(x1, 0.2)) + 0.7 * torch.nn.functional.normalize(lr(x2, 0.2))
+    assert out.shape == (n, 2 * d)
+    assert rel(out[:, :d].cpu().numpy(), z.double().cpu().numpy()) < 1e-6
+    assert rel(out[:, d:].cpu().numpy(), (z + y).double().cpu().numpy()) < 1e-6
+    out1 = ops.rows_normalize_mix(x1, x2, 1.0, 0.0)  # no y, identity activation
+    assert out1.shape == (n, d)
+    assert rel(out1.cpu().numpy(), torch.nn.functional.normalize(x1).double().cpu().numpy()) < 1e-6
+
+
+def test_spmm_linearity_and_adjoint_large(ops):
+    """Properties that hold at any size: A(x + 2y) = Ax + 2Ay and <Ax, z> = <x, A'z> (power-law rows, 4M nnz)."""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(3)
+    n_rows, n_cols, nnz, d = 150_000, 90_000, 4_000_000, 64
+    w = torch.rand(n_rows, device="cuda", generator=g) ** 6          # heavy-tailed row degrees
+    rows = torch.multinomial(w, nnz, replacement=True, generator=g)
+    cols = torch.randint(0, n_cols, (nnz,), device="cuda", generator=g)
+    val = torch.rand(nnz, device="cuda", generator=g)
+    a = ops.GraphCSR.from_coo(torch.stack([rows, cols]), val, (n_rows, n_cols), torch.device("cuda"))
+    assert a.plan_stats()["split_rows"] > 0                          # long rows are cut into chunks
+    x = torch.randn(n_cols, d, device="cuda", generator=g)
+    y = torch.randn(n_cols, d, device="cuda", generator=g)
+    z = torch.randn(n_rows, d, device="cuda", generator=g)
+    ax, ay, axy = ops.spmm_raw(a, x), ops.spmm_raw(a, y), ops.spmm_raw(a, x + 2 * y)
+    assert rel(axy.cpu().numpy(), (ax.double() + 2 * ay.double()).cpu().numpy()) < 1e-5
+    atz = ops.spmm_raw(a.t(), z)
+    lhs, rhs = (ax.double() * z.double()).sum().item(), (x.double() * atz.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), abs(rhs), 1.0)
+    again = ops.spmm_raw(a, x)
+    assert torch.equal(ax, again)                                    # run-to-run deterministic
+
+
+def test_score_modes_agree_large(ops):
+    """All three precisions return identical ids and scores on a catalogue of 300k items (popularity-skewed norms)."""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(4)
+    b, n_items, d, k = 1500, 300_000, 64, 50
+    scale = torch.exp(1.0 * torch.randn(n_items, 1, device="cuda", generator=g))
+    ei = torch.randn(n_items, d, device="cuda", generator=g) * scale
+    eu = torch.randn(b, d, device="cuda", generator=g)
+    lens = torch.randint(0, 80, (b,), device="cuda", generator=g)
+    mrp = torch.zeros(b + 1, dtype=torch.int64, device="cuda")
+    mrp[1:] = torch.cumsum(lens, 0)
+    total = int(mrp[-1])
+    rid = torch.repeat_interleave(torch.arange(b, device="cuda"), lens)
+    key = torch.unique(rid * n_items + torch.randint(0, n_items, (total,), device="cuda", generator=g))
+    mrp = torch.searchsorted(key, torch.arange(b + 1, device="cuda") * n_items)
+    mit = (key % n_items).to(torch.int32)
+    res = {p: ops.score_mask_topk(eu, ei, k, mask_rowptr=mrp, mask_items=mit, precision=p) for p in ("fp32", "tc", "tc_split")}
+    for p in ("tc", "tc_split"):
+        assert torch.equal(res[p][0], res["fp32"][0]), p
+        assert torch.equal(res[p][1], res["fp32"][1]), p
