@@ -106,7 +106,9 @@ class ClockSampler(object):
 
 
 class HostInputs(object):
-    """The per-step inputs of an evaluation pass in pinned host memory + their device landing buffers."""
+    """The per-step inputs of an evaluation pass in pinned host memory + their device landing buffers.  `upload()`
+    enqueues the copies on a side stream; the first access to a device tensor makes the consuming stream wait for them,
+    so the transfer overlaps whatever the consumer does before touching its inputs (the propagation)."""
 
     FIELDS = ("eval_u", "mask_rowptr", "mask_items", "gt_rowptr", "gt_items")
 
@@ -115,14 +117,22 @@ class HostInputs(object):
         self.dev = {k: torch.empty_like(getattr(loader, k), device=device) for k in self.FIELDS}
         self.eval_len_list = loader.eval_len_list
         self.bytes = sum(v.numel() * v.element_size() for v in self.host.values())
+        self.stream = torch.cuda.Stream(device=device)
+        self.pending = False
 
     def upload(self):
-        for k in self.FIELDS:
-            self.dev[k].copy_(self.host[k], non_blocking=True)
+        self.stream.wait_stream(torch.cuda.current_stream())  # after every earlier consumer of the landing buffers
+        with torch.cuda.stream(self.stream):
+            for k in self.FIELDS:
+                self.dev[k].copy_(self.host[k], non_blocking=True)
+        self.pending = True
         return self
 
     def __getattr__(self, k):
         if k in HostInputs.FIELDS:
+            if self.pending:
+                torch.cuda.current_stream().wait_stream(self.stream)
+                self.pending = False
             return self.dev[k]
         raise AttributeError(k)
 
@@ -211,11 +221,15 @@ def run_gpu(args):
             dist.all_reduce(sums)
         return sums
 
-    def step_e2e():
+    def enqueue_e2e():
         sums = hot_path(host_in.upload())
         if world > 1:
             dist.all_reduce(sums)
         sums_host.copy_(sums, non_blocking=True)
+        return sums_host
+
+    def step_e2e():
+        enqueue_e2e()
         torch.cuda.current_stream().synchronize()
         return sums_host
 
@@ -225,10 +239,17 @@ def run_gpu(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, profile=False):
+    use_graph = world == 1 and not args.no_graph
+
+    def timed(fn, steps, warmup, profile=False, graph=False, sync_each=False):
         for _ in range(warmup):
             fn()
         barrier()
+        run = trainer.graphed(fn) if graph else fn
+        if graph:
+            for _ in range(2):
+                run()
+            barrier()
         if profile:
             ops.PROFILE = []
         launches0 = ops.LAUNCHES
@@ -239,7 +260,9 @@ def run_gpu(args):
                 flush_buf.fill_(1)  # L2 flush between timed iterations (outside the per-step events)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            fn()
+            run()
+            if sync_each:
+                torch.cuda.current_stream().synchronize()  # the step's result has reached host memory
             b.record()
             evs.append((a, b))
         barrier()
@@ -255,9 +278,13 @@ def run_gpu(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_total, wall, launches, prof = timed(step_resident, args.steps, args.warmup, profile=True)
+    # timed region: the step replayed from a CUDA graph (single GPU; eager launches otherwise).  Per-kernel durations
+    # and the launch count come from a separate eager pass with CUDA events around every operator.
+    ms_total, wall, launches, _ = timed(step_resident, args.steps, args.warmup, graph=use_graph)
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e, _, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    ms_eager, _, launches, prof = timed(step_resident, args.steps, 1, profile=True)
+    ms_e2e, _, _, _ = timed(enqueue_e2e if use_graph else step_e2e, args.steps, max(1, args.warmup // 2), graph=use_graph,
+                            sync_each=use_graph)
     if os.environ.get("GMR_PROFILE_STEP"):  # ncu --profile-from-start off: exactly one resident step is captured
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStart()
@@ -334,6 +361,7 @@ def run_gpu(args):
                        "n_items": wl.n_items, "nnz_train": wl.nnz_train, "eval_users": n_eval_total, "topk": k,
                        "embedding_size": cfg["embedding_size"], "n_layers": cfg["n_layers"],
                        "score_precision": args.precision,
+                       "launch": "CUDA graph replay of the whole step" if use_graph else "eager launches",
                        "parallelism": ("row-sharded propagation (push-SpMM all-gather) + user-block sharded eval, x%d" % world)
                        if world > 1 else "single GPU",
                        "l2": ("L2 flushed between timed steps (operands fit the %d MB L2)" % (l2_bytes >> 20)) if need_flush
@@ -343,7 +371,7 @@ def run_gpu(args):
             "e2e": {"value": n_eval_total / (ms_e2e / args.steps) * 1e3, "unit": "users/s",
                     "h2d_bytes_per_step": host_in.bytes * world, "d2h_bytes_per_step": int(sums_host.numel() * 8),
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": wall, "setup_s": setup_s,
+            "gpu_launches": launches, "eager_ms_per_step": ms_eager / args.steps, "clocks": clocks, "wall_s_timed_region": wall, "setup_s": setup_s,
             "metrics": result_dict,
         }
     return out, wl, trainer, full_loader
@@ -473,6 +501,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("GMR_SCORE_PRECISION", "tc"), choices=["fp32", "tc"],
                     help="scoring path: tc = tcgen05 split-bf16 + exact re-rank (same ids/scores as fp32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay of the step")
     ap.add_argument("--no-extra-workloads", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

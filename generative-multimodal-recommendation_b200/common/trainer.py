@@ -39,6 +39,10 @@ class Trainer(object):
         if self.eval_mode == "batched":
             outs = [self.model.full_sort_topk(batch, k) for batch in eval_data]
             return torch.cat(outs, dim=0).to(torch.int32), None
+        try:
+            self.model.cached_propagate()  # before the loader's tensors are touched: an in-flight upload overlaps it
+        except NotImplementedError:
+            pass                           # models that score through eval_factors only (LD4MRec)
         eu, rows, ei, bias = self.model.eval_factors(eval_data.eval_u)
         ids, sc = ops.score_mask_topk(eu.contiguous(), ei.contiguous(), k, users=rows, bias=bias,
                                       mask_rowptr=eval_data.mask_rowptr, mask_items=eval_data.mask_items,
@@ -49,6 +53,29 @@ class Trainer(object):
     def evaluate(self, eval_data, is_test=False, idx=0):
         ids, _ = self.topk_all(eval_data)
         return self.evaluator.evaluate(ids, eval_data, is_test=is_test, idx=idx)
+
+    def graphed(self, fn):
+        """Capture ``fn`` (a no-argument callable that only enqueues GPU work, e.g. one evaluation pass) into a CUDA
+        graph and return ``replay() -> whatever fn returned at capture`` (static tensors, refreshed by every replay).
+        Evaluation at the Amazon shapes is launch-bound (~60 launches for <1 ms of GPU work): one graph launch
+        replaces them.  ``fn`` must have run at least once before (workspaces, plans and caches are created
+        eagerly) and must not synchronise."""
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn()                                   # one more eager run on the capture side stream
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = fn()
+
+        def replay():
+            graph.replay()
+            return out
+
+        replay.graph = graph
+        return replay
 
     def fit(self, *args, **kwargs):
         raise NotImplementedError("training loops are outside the hot path this package accelerates; use "

@@ -399,16 +399,32 @@ __device__ __forceinline__ void final_sort_write(uint64_t (&ek)[NSORT], int lane
 }
 
 // exact fp32 score of the item at sweep position p: the same sequential fmaf chain as the fp32 kernel and
-// the oracle (bit-exact), with the 64 floats of each block of the item row loaded up front (one memory
-// latency per block instead of one per element) and the user row read from shared memory.
-__device__ __forceinline__ uint64_t exact_key(const ScrArgs& a, const float* __restrict__ u_sm, uint32_t p)
+// the oracle (bit-exact).  The user row is read from shared memory; the item row comes from the CTA's
+// shared-memory copy of the `n_hot` highest-norm rows when p < n_hot (where nearly every candidate of a
+// popularity-skewed catalogue lives: 32 lanes gathering 32 different 256-byte rows from global memory cost 32 L1
+// wavefronts per load instruction, from padded shared memory ~6), otherwise from global memory with the 64 floats of
+// each block loaded up front (one memory latency per block instead of one per element).
+__device__ __forceinline__ uint64_t exact_key(const ScrArgs& a, const float* __restrict__ u_sm, uint32_t p,
+                                              const float* __restrict__ e_hot, int n_hot, int hot_pitch)
 {
     const int item = a.perm[p];
-    const float* e = a.Ei + (int64_t)item * a.lde_i;
     float s = a.bias ? a.bias[item] : 0.f;
+    const float4* u4 = reinterpret_cast<const float4*>(u_sm);
+    if ((int)p < n_hot) {
+        const float4* e4 = reinterpret_cast<const float4*>(e_hot + (size_t)p * hot_pitch);
+        for (int d = 0; d < a.D / 4; ++d) {
+            const float4 ev = e4[d];
+            const float4 uv = u4[d];
+            s = fmaf(uv.x, ev.x, s);
+            s = fmaf(uv.y, ev.y, s);
+            s = fmaf(uv.z, ev.z, s);
+            s = fmaf(uv.w, ev.w, s);
+        }
+        return make_key(s, item);
+    }
+    const float* e = a.Ei + (int64_t)item * a.lde_i;
     if (a.vec4) {
         const float4* e4 = reinterpret_cast<const float4*>(e);
-        const float4* u4 = reinterpret_cast<const float4*>(u_sm);
         for (int d0 = 0; d0 < a.D / 4; d0 += 16) {
             float4 ev[16];
 #pragma unroll
@@ -430,13 +446,14 @@ __device__ __forceinline__ uint64_t exact_key(const ScrArgs& a, const float* __r
 
 template <int NSORT>
 __device__ __forceinline__ void rescore_sort_write(const ScrArgs& a, const float* __restrict__ u_sm,
-                                                   const uint64_t* __restrict__ s_row, int cnt, int lane, int64_t rb)
+                                                   const uint64_t* __restrict__ s_row, int cnt, int lane, int64_t rb,
+                                                   const float* __restrict__ e_hot, int n_hot, int hot_pitch)
 {
     uint64_t ek[NSORT];
 #pragma unroll
     for (int c = 0; c < NSORT; ++c) {
         const int j = c * 32 + lane;
-        ek[c] = (j < cnt) ? exact_key(a, u_sm, (uint32_t)s_row[j]) : 0ull;
+        ek[c] = (j < cnt) ? exact_key(a, u_sm, (uint32_t)s_row[j], e_hot, n_hot, hot_pitch) : 0ull;
     }
     final_sort_write<NSORT>(ek, lane, a, rb);
 }
@@ -809,45 +826,59 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// ---- 3c. finalisation: one warp per row at full occupancy ---------------------------------------------
+// ---- 3c. finalisation: one warp per row, persistent CTAs ---------------------------------------------
 // Last prune if anything was appended since the previous one, exact fp32 re-score of the survivors, sort by
-// (score desc, id asc), write the top K; undecidable rows are queued for the fp32 kernel.
+// (score desc, id asc), write the top K; undecidable rows are queued for the fp32 kernel.  Each CTA first copies the
+// `n_hot` highest-norm item rows (sweep positions 0 .. n_hot-1) into padded shared memory.
 template <int NPL>
 __global__ void __launch_bounds__(256)
-    score_screen_finalize_kernel(ScrArgs a)
+    score_screen_finalize_kernel(ScrArgs a, int n_hot)
 {
     constexpr int CAP = 32 * NPL;
-    __shared__ __align__(16) float u_sm[8][256];
+    extern __shared__ __align__(16) float fin_smem[];
+    const int hot_pitch = a.D + 4;                      // +16 B: conflict-free 128-bit reads of 8 different rows
+    float* u_all = fin_smem;                            // [8][D]
+    float* e_hot = fin_smem + 8 * a.D;                  // [n_hot][D + 4]
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + w;
-    if (b >= a.B) return;
-    const RowConst rc = a.row_const[b];
-    int64_t mlo, mhi;
-    const bool fe = row_force_exact(a, b, mlo, mhi);
-    int cnt = a.row_cnt[b];
-    const int chk = a.row_chk[b];
-    uint64_t* s_row = a.slots + b * CAP;
-    bool fallback = fe || cnt < a.K;
-    if (!fallback && cnt != chk) {  // appended since the last prune
-        const PruneResult pr = screen_prune<NPL>(s_row, cnt, chk, rc.ce, rc.ab, a.nb, a.perm, a.mask_items, mlo, mhi, a.K, lane,
-                                                 a.stats);
-        cnt = pr.cnt;
-        fallback = cnt < a.K;  // overflow (-1) or too few unmasked candidates
+    for (int idx = threadIdx.x; idx < n_hot * (a.D / 4); idx += blockDim.x) {
+        const int p = idx / (a.D / 4), j = idx - p * (a.D / 4);
+        const int item = a.perm[p];
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (item >= 0) v = __ldg(reinterpret_cast<const float4*>(a.Ei + (int64_t)item * a.lde_i) + j);
+        *reinterpret_cast<float4*>(e_hot + (size_t)p * hot_pitch + 4 * j) = v;
     }
-    if (fallback) {
-        if (lane == 0) a.fallback_rows[atomicAdd(a.fallback_count, 1)] = (int32_t)b;
-        return;
+    __syncthreads();
+    float* u_sm = u_all + w * a.D;
+    for (int64_t b = (int64_t)blockIdx.x * 8 + w; b < a.B; b += (int64_t)gridDim.x * 8) {
+        const RowConst rc = a.row_const[b];
+        int64_t mlo, mhi;
+        const bool fe = row_force_exact(a, b, mlo, mhi);
+        int cnt = a.row_cnt[b];
+        const int chk = a.row_chk[b];
+        uint64_t* s_row = a.slots + b * CAP;
+        bool fallback = fe || cnt < a.K;
+        if (!fallback && cnt != chk) {  // appended since the last prune
+            const PruneResult pr = screen_prune<NPL>(s_row, cnt, chk, rc.ce, rc.ab, a.nb, a.perm, a.mask_items, mlo, mhi,
+                                                     a.K, lane, a.stats);
+            cnt = pr.cnt;
+            fallback = cnt < a.K;  // overflow (-1) or too few unmasked candidates
+        }
+        if (fallback) {
+            if (lane == 0) a.fallback_rows[atomicAdd(a.fallback_count, 1)] = (int32_t)b;
+            continue;
+        }
+        const float* urow = a.Eu + (a.users ? a.users[b] : b) * a.lde_u;
+        __syncwarp();
+        for (int d = lane; d < a.D; d += 32) u_sm[d] = urow[d];
+        __syncwarp();
+        if (a.stats && lane == 0) atomicAdd(&a.stats[5], (unsigned long long)cnt);
+        if (cnt <= 64)
+            rescore_sort_write<2>(a, u_sm, s_row, cnt, lane, b, e_hot, n_hot, hot_pitch);
+        else if (cnt <= 128)
+            rescore_sort_write<4>(a, u_sm, s_row, cnt, lane, b, e_hot, n_hot, hot_pitch);
+        else
+            rescore_sort_write<NPL>(a, u_sm, s_row, cnt, lane, b, e_hot, n_hot, hot_pitch);
     }
-    const float* urow = a.Eu + (a.users ? a.users[b] : b) * a.lde_u;
-    for (int d = lane; d < a.D; d += 32) u_sm[w][d] = urow[d];
-    __syncwarp();
-    if (a.stats && lane == 0) atomicAdd(&a.stats[5], (unsigned long long)cnt);
-    if (cnt <= 64)
-        rescore_sort_write<2>(a, u_sm[w], s_row, cnt, lane, b);
-    else if (cnt <= 128)
-        rescore_sort_write<4>(a, u_sm[w], s_row, cnt, lane, b);
-    else
-        rescore_sort_write<NPL>(a, u_sm[w], s_row, cnt, lane, b);
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -1056,6 +1087,17 @@ int score_topk_screen_launch(const float* Eu, int64_t lde_u, const int64_t* user
     const int grid = scr_grid(B);
     const int npl = scr_npl(K);
     const int row_blocks = (B + 7) / 8;
+    // finalisation: persistent CTAs (2 per SM) that stage the n_hot highest-norm item rows in shared memory
+    int n_hot = 0;
+    if (a.vec4) {
+        for (n_hot = 256; n_hot > 0; n_hot >>= 1)
+            if ((size_t)n_hot * (D + 4) * 4 + 8 * (size_t)D * 4 <= 100 * 1024) break;
+        if (n_hot > L.i_pad) n_hot = L.i_pad;
+    }
+    const size_t fin_smem = (size_t)n_hot * (D + 4) * 4 + 8 * (size_t)D * 4;
+    int fin_ctas_per_sm = (int)((220 * 1024) / (fin_smem > 0 ? fin_smem : 1));
+    fin_ctas_per_sm = fin_ctas_per_sm < 1 ? 1 : (fin_ctas_per_sm > 3 ? 3 : fin_ctas_per_sm);
+    const int fin_grid = row_blocks < fin_ctas_per_sm * sm_count() ? row_blocks : fin_ctas_per_sm * sm_count();
     // phase 0 sweep -> checkpoint (mask + first L, per row at full occupancy) -> phase 1 sweep for the groups that
     // still need tiles -> finalisation (exact re-score + sort, per row at full occupancy)
 #define GMR_SCR_LAUNCH(NPL, BIAS)                                                                                  \
@@ -1071,7 +1113,9 @@ int score_topk_screen_launch(const float* Eu, int64_t lde_u, const int64_t* user
         score_screen_sweep_kernel<NPL, BIAS><<<grid, kScrThreads, smem, st>>>(map_a, map_b, a, 1);                 \
         GMR_LAUNCH_CHECK();                                                                                        \
         if (a.debug == 0 || a.debug == 3) {                                                                        \
-            score_screen_finalize_kernel<NPL><<<row_blocks, 256, 0, st>>>(a);                                      \
+            GMR_CHECK_CUDA(cudaFuncSetAttribute(score_screen_finalize_kernel<NPL>,                                 \
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));      \
+            score_screen_finalize_kernel<NPL><<<fin_grid, 256, fin_smem, st>>>(a, n_hot);                          \
             GMR_LAUNCH_CHECK();                                                                                    \
         }                                                                                                          \
     } while (0)

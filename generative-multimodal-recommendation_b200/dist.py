@@ -151,14 +151,16 @@ def all_gather_rows(local, sizes, group=None):
 class ShardedDiffMM(object):
     """Row-sharded ``forward_MM`` of a DiffMM model replica (parameters replicated, graphs sharded).
 
-    Rank g owns users [u0, u1) and items [i0, i1).  Dataflow (fused form):
+    Rank g owns users [u0, u1) and items [i0, i1).  Same regrouped dataflow as the single-GPU
+    ``DiffMM._forward_mm_fused``, cut by output rows:
 
-        Xi[i-block]   = [F_v | F_t]                    sharded projection, NCCL all-gather   -> Xi  [I, 128]
-        [H_v | H_t]_g = R_hat[g] . Xi                  K1 PUSH into every peer's Xu[:, 0:128] (fused all-gather)
-        G_g           = R_hat[g] . I0                  K1, local
-        [G_v|G_t|H]_g = R_hat'[g] . Xu                 K1, local  (Xu = [H_v | H_t | U0], [U, 192])
-        P_m,g         = A_m[g] . [U0; I0]              K1, local  (modality graphs, both row blocks)
-        M_g           -> NCCL all-gather -> M [N, 64];  L_g = A[g] . M   (K1; pushed when more layers follow)
+        [Z | Z + I0][i-block]   sharded projections + gmr_rows_normalize_mix     NCCL all-gather -> Xi [I, 2d]
+        Hz_g      = R_hat[g] . Z            K1 PUSH into every peer's Hz [U, d]   (fused all-gather over NVLink)
+        modal_u,g = R_hat[g] . (Z + I0)     K1, local
+        modal_i,g = R_hat'[g] . (U0 + Hz)   K1, local
+        modal_g  += lambda (w0 A_v + w1 A_t)[g] . [U0; I0]                        K1, local, in place
+        modal     = NCCL all-gather of the row blocks;   L_g = A[g] . modal       K1, local
+        E_g       = modal_g + L_g + ris_lambda n(modal_g)
 
     and the result rows (users of the block, items of the block) are returned with the block bounds.
     """
@@ -180,78 +182,78 @@ class ShardedDiffMM(object):
         self.u0, self.u1, self.i0, self.i1 = self.ub[g], self.ub[g + 1], self.ib[g], self.ib[g + 1]
         self.r_ui = adj.ui.row_block(self.u0, self.u1)       # [U_g, I]
         self.r_iu = adj.iu.row_block(self.i0, self.i1)       # [I_g, U]
-        self.xu = PeerBuffer(nu, 3 * d, self.dev, group)     # [H_v | H_t | U0], gathered by the push SpMM
+        self.hz = PeerBuffer(nu, d, self.dev, group)         # R_hat Z, gathered by the push SpMM
         self.token = torch.zeros(1, device=self.dev)
         self._graphs_version = None
+        self._mix_sig = None
 
-    def _modality_blocks(self):
+    def _graph_blocks(self, w0, w1):
         m = self.model
-        if self._graphs_version != m._graph_version:
-            nu = m.n_users
-            self.img_u = m.image_UI_matrix.row_block(self.u0, self.u1)
-            self.img_i = m.image_UI_matrix.row_block(nu + self.i0, nu + self.i1)
-            self.txt_u = m.text_UI_matrix.row_block(self.u0, self.u1)
-            self.txt_i = m.text_UI_matrix.row_block(nu + self.i0, nu + self.i1)
-            full = m.norm_adj.full
+        nu = m.n_users
+        full = m.norm_adj.full
+        if self._graphs_version is not full:
             self.adj_u = full.row_block(self.u0, self.u1)
             self.adj_i = full.row_block(nu + self.i0, nu + self.i1)
-            self._graphs_version = m._graph_version
+            self._graphs_version = full
+        mix = m._modal_mix_graph(m.image_UI_matrix, m.text_UI_matrix, w0, w1)
+        sig = (w0, w1, m.ris_adj_lambda, id(mix))
+        if self._mix_sig != sig:
+            self.mix_u = mix.row_block(self.u0, self.u1)
+            self.mix_i = mix.row_block(nu + self.i0, nu + self.i1)
+            self._mix_sig = sig
         return self
 
     @torch.no_grad()
     def forward_MM(self):
-        import torch.distributed as dist
-        import torch.nn.functional as F
-
         m = self.model
-        self._modality_blocks()
         nu, ni, d = m.n_users, m.n_items, m.latdim
         u0, u1, i0, i1 = self.u0, self.u1, self.i0, self.i1
-        U0, I0 = m.uEmbeds.detach(), m.iEmbeds.detach()
-        weight = m.softmax(m.modal_weight)
-        # 1. sharded projections -> gathered Xi = [F_v | F_t]
-        fv = F.normalize(m.leakyrelu(torch.mm(m.v_feat[i0:i1], m.image_trans)))
-        ft = F.normalize(m.leakyrelu(torch.mm(m.t_feat[i0:i1], m.text_trans)))
-        xi_local = torch.cat([fv, ft], dim=1)
+        w0, w1 = m._modal_weights_host()
+        self._graph_blocks(w0, w1)
+        e0 = m._packed_e0()
+        U0, I0 = e0[:nu], e0[nu:]
         usz = [self.ub[g + 1] - self.ub[g] for g in range(self.world)]
         isz = [self.ib[g + 1] - self.ib[g] for g in range(self.world)]
+        # 1. sharded projections -> gathered Xi = [Z | Z + I0]
+        pv = torch.mm(m.v_feat[i0:i1], m.image_trans.detach())
+        pt = torch.mm(m.t_feat[i0:i1], m.text_trans.detach())
+        xi_local = ops.rows_normalize_mix(pv, pt, w0, w1, y=I0[i0:i1], slope=m.leakyrelu.negative_slope)
         xi = all_gather_rows(xi_local, isz, self.group)
-        # 2. user rows: [H_v | H_t] pushed to every replica of Xu (fused all-gather), G local
-        xu = self.xu.tensor
-        xu[:, 2 * d:] = U0
-        spmm_push(self.r_ui, xi, self.xu.ptr_table, self.world, u0, 3 * d)
-        g_u = ops.spmm_raw(self.r_ui, I0)
+        # 2. user rows: R_hat Z pushed to every replica of Hz (fused all-gather); modal_u stays local
+        spmm_push(self.r_ui, xi[:, :d], self.hz.ptr_table, self.world, u0, d)
+        modal_u = ops.spmm_raw(self.r_ui, xi[:, d:])
         stream_barrier(self.token)
-        # 3. item rows: [G_v | G_t | H] = R_hat' . [H_v | H_t | U0]
-        yi = ops.spmm_raw(self.r_iu, xu)
-        # 4. modality graphs
-        e0 = torch.cat([U0, I0])
-        p_img_u, p_img_i = ops.spmm_raw(self.img_u, e0), ops.spmm_raw(self.img_i, e0)
-        p_txt_u, p_txt_i = ops.spmm_raw(self.txt_u, e0), ops.spmm_raw(self.txt_i, e0)
-        lam = m.ris_adj_lambda
-        hv_u, ht_u = xu[u0:u1, 0:d], xu[u0:u1, d:2 * d]
-        e_img_u = (hv_u + g_u) + lam * p_img_u
-        e_txt_u = (ht_u + g_u) + lam * p_txt_u
-        e_img_i = (yi[:, 2 * d:] + yi[:, 0:d]) + lam * p_img_i
-        e_txt_i = (yi[:, 2 * d:] + yi[:, d:2 * d]) + lam * p_txt_i
-        m_u = weight[0] * e_img_u + weight[1] * e_txt_u
-        m_i = weight[0] * e_img_i + weight[1] * e_txt_i
+        # 3. item rows: modal_i = R_hat' (U0 + R_hat Z)
+        xu = torch.add(U0, self.hz.tensor)
+        modal_i = ops.spmm_raw(self.r_iu, xu)
+        stream_barrier(self.token)   # nobody may overwrite Hz (next call) before every rank has read it
+        # 4. modality graphs, accumulated in place
+        ops.spmm_raw(self.mix_u, e0, out=modal_u, beta=1.0)
+        ops.spmm_raw(self.mix_i, e0, out=modal_i, beta=1.0)
         # 5. GCN layers over the full adjacency
-        acc_u, acc_i = m_u, m_i
-        last_u, last_i = m_u, m_i
-        for _ in range(m.gnn_layer):
+        acc_u = acc_i = None
+        last_u, last_i = modal_u, modal_i
+        for layer in range(m.gnn_layer):
             full = torch.cat([all_gather_rows(last_u, usz, self.group), all_gather_rows(last_i, isz, self.group)])
             last_u, last_i = ops.spmm_raw(self.adj_u, full), ops.spmm_raw(self.adj_i, full)
-            acc_u, acc_i = acc_u + last_u, acc_i + last_i
-        out_u = acc_u + m.ris_lambda * F.normalize(m_u)
-        out_i = acc_i + m.ris_lambda * F.normalize(m_i)
-        return out_u, out_i
+            if layer == 0:
+                acc_u = ops.rows_axpby_norm(modal_u, last_u, modal_u, a=1.0, b=1.0, c=m.ris_lambda)
+                acc_i = ops.rows_axpby_norm(modal_i, last_i, modal_i, a=1.0, b=1.0, c=m.ris_lambda)
+            else:
+                ops.rows_axpby_norm(acc_u, last_u, None, a=1.0, b=1.0, out=acc_u)
+                ops.rows_axpby_norm(acc_i, last_i, None, a=1.0, b=1.0, out=acc_i)
+        if acc_u is None:
+            acc_u = ops.rows_axpby_norm(modal_u, None, modal_u, a=1.0, c=m.ris_lambda)
+            acc_i = ops.rows_axpby_norm(modal_i, None, modal_i, a=1.0, c=m.ris_lambda)
+        return acc_u, acc_i
+
+    def close(self):
+        """Release the peer-mapped buffers (CUDA IPC mappings of the other ranks' replicas)."""
+        self.hz.close()
 
     @torch.no_grad()
     def eval_factors(self):
         """(user rows of this rank's block, full item table): the item block is all-gathered."""
-        import torch.distributed as dist
-
         out_u, out_i = self.forward_MM()
         isz = [self.ib[g + 1] - self.ib[g] for g in range(self.world)]
         return out_u, all_gather_rows(out_i, isz, self.group)

@@ -78,4 +78,4 @@ def test_sharded_diffmm_world1_equals_model(mods):
     assert np.abs(su.cpu().numpy() - z["emb/user"]).max() / np.abs(z["emb/user"]).max() < 1e-5
     part = gd.shard_eval_by_user_block(loaders["valid"], 100, 200)
     assert part.eval_u.numel() > 0 and int(part.eval_u.max()) < 100
-    sh.xu.close()
+    sh.close()

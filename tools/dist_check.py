@@ -59,7 +59,7 @@ def main():
            "user_rows_rel_err": tol_u, "gathered_items_rel_err": tol_i, "topk_rows_identical": same_rows,
            "metric_sums_match": ok_m}
     print(json.dumps(res), flush=True)
-    sh.xu.close()
+    sh.close()
     dist.barrier()
     dist.destroy_process_group()
     if not (ok_u and ok_i and ok_ids and ok_m):
