@@ -116,11 +116,6 @@ __global__ void __launch_bounds__(kWarps * 32, (ITER == 1) ? 4 : 2)
     __shared__ int2 stage[kWarps][STAGE];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t v = (int64_t)blockIdx.x * kWarps + warp;
-    if (v >= n_vrows) return;  // whole warp leaves together; only __syncwarp below
-
-    const int begin = vptr[v], end = vptr[v + 1];
-    const int dst = IDENT ? (int)v : vrow[v];
     const int sub = lane % LANES, grp = lane / LANES;
     const int vcol0 = blockIdx.y * (LANES * ITER) + sub;  // this lane's first Vec column
     const uint32_t ldv = (uint32_t)(ldx / VEC);           // row pitch in Vec units (OFF32 only)
@@ -130,6 +125,13 @@ __global__ void __launch_bounds__(kWarps * 32, (ITER == 1) ? 4 : 2)
     for (int it = 0; it < ITER; ++it) colok[it] = EXACT || (vcol0 + it * LANES < DV);
 
     const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+    // Persistent warps: every warp walks virtual rows v, v + W, v + 2W, ... (W = warps in the grid).  Row lengths are
+    // power-law distributed; with one virtual row per warp a CTA stays resident until its longest row is done and the
+    // SM runs at a third of its warp slots (ncu: 32 % warps active).  Striding keeps every slot busy until the tail.
+    const int64_t n_warps_grid = (int64_t)gridDim.x * kWarps;
+    for (int64_t v = (int64_t)blockIdx.x * kWarps + warp; v < n_vrows; v += n_warps_grid) {
+    const int begin = vptr[v], end = vptr[v + 1];
+    const int dst = IDENT ? (int)v : vrow[v];
     Vec acc[ITER];
 #pragma unroll
     for (int it = 0; it < ITER; ++it) acc[it] = Ops::zero();
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(kWarps * 32, (ITER == 1) ? 4 : 2)
 #pragma unroll
         for (int it = 0; it < ITER; ++it) acc[it] = Ops::xor_add(acc[it], 16);
     }
-    if (grp != 0) return;
+    if (grp != 0) continue;
 
 #pragma unroll
     for (int it = 0; it < ITER; ++it) {
@@ -219,6 +221,7 @@ __global__ void __launch_bounds__(kWarps * 32, (ITER == 1) ? 4 : 2)
             *y = (beta == 0.f) ? Ops::scale(alpha, acc[it]) : Ops::axpby(alpha, acc[it], beta, *y);
         }
     }
+    }  // persistent loop over virtual rows
 }
 
 // One CTA per split row: warp w sums the slots of its fixed sub-range in order, the eight warp
@@ -271,7 +274,10 @@ static int launch_vrow2(const gmr_spmm_plan* plan, const int32_t* rowptr, const 
     const bool ident = plan->d_vptr == nullptr;
     const int64_t nv = plan->n_vrows;
     if (nv == 0) return GMR_OK;
-    dim3 grid((unsigned)((nv + kWarps - 1) / kWarps), (unsigned)((DV + LANES * ITER - 1) / (LANES * ITER)));
+    // persistent grid: enough CTAs to fill every SM's warp slots (8 CTAs x 8 warps), never more than the work
+    const int64_t want = (nv + kWarps - 1) / kWarps;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)((DV + LANES * ITER - 1) / (LANES * ITER)));
     dim3 block(kWarps * 32);
     if (ident)
         spmm_vrow_kernel<Vec, LANES, ITER, true, PUSH, OFF32, EXACT><<<grid, block, 0, st>>>(
