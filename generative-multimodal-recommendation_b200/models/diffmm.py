@@ -118,6 +118,14 @@ class DiffMM(GeneralRecommender):
             return self._forward_mm_fused(adj, as_graph(image_adj), as_graph(text_adj))
         return self._forward_mm_literal(as_graph(adj), as_graph(image_adj), as_graph(text_adj))
 
+    @staticmethod
+    def _project(feat, weight):
+        """feat @ weight: the split-TF32 tcgen05 kernel when the shape fits it (N = 64, K % 32 == 0), else the library
+        GEMM the reference calls (torch.mm)."""
+        if ops.dense_proj_supported(feat, weight):
+            return ops.dense_proj(feat, weight)
+        return torch.mm(feat, weight)
+
     def _modal_weights_host(self):
         """softmax(modal_weight) as two Python floats, re-read from the device only when the parameter changed."""
         sig = (id(self.modal_weight), self.modal_weight._version)
@@ -186,8 +194,8 @@ class DiffMM(GeneralRecommender):
         e0 = self._packed_e0()
         u0, i0 = e0[:nu], e0[nu:]
         ev = ops._prof_begin()
-        pv = torch.mm(self.v_feat, self.image_trans.detach())     # dense projections: library GEMMs
-        pt = torch.mm(self.t_feat, self.text_trans.detach())
+        pv = self._project(self.v_feat, self.image_trans.detach())   # dense projections
+        pt = self._project(self.t_feat, self.text_trans.detach())
         ops._prof_end("dense_projections", ev, flops=2.0 * ni * d * (self.image_feat_dim + self.text_feat_dim),
                       bytes=4.0 * ni * (self.image_feat_dim + self.text_feat_dim + 2 * d))
         xi = rows_normalize_mix(pv, pt, w0, w1, y=i0, slope=self.leakyrelu.negative_slope)   # [I, 2d] = Z | Z + I0

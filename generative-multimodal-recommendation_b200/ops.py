@@ -260,6 +260,34 @@ def rows_normalize_mix(x1, x2, w1, w2, y=None, slope=1.0, eps=1e-12, out=None):
     return out
 
 
+def dense_proj_supported(a, w):
+    k, n = int(w.shape[0]), int(w.shape[1])
+    return (n == 64 and k % 32 == 0 and a.dim() == 2 and a.shape[1] == k and a.stride(1) == 1 and a.stride(0) % 4 == 0
+            and a.data_ptr() % 16 == 0 and a.dtype == torch.float32 and w.dtype == torch.float32)
+
+
+def dense_proj(a, w, out=None):
+    """C = A @ W (fp32, fp32-level accuracy) through the split-TF32 tcgen05 kernel (K3 family).  A [M, K] with
+    contiguous rows, W [K, 64].  Shapes the kernel does not take (N != 64, K % 32 != 0) raise; callers that want the
+    library GEMM for those check ``dense_proj_supported`` first."""
+    global LAUNCHES
+    lib = _lib.load()
+    m, k, n = int(a.shape[0]), int(a.shape[1]), int(w.shape[1])
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    ap, lda = _rows(a, "A")
+    wc = w if (w.stride(1) == 1) else w.contiguous()
+    wp, ldw = _rows(wc, "W")
+    cp, ldc = _rows(out, "C")
+    need = lib.gmr_dense_proj_workspace_bytes(k, n)
+    ws = _ws(a.device, need, "proj")
+    with torch.cuda.device(a.device):
+        _lib.check(lib.gmr_dense_proj_f32(ap, lda, m, k, wp, ldw, n, cp, ldc, _ptr(ws), need, _stream()),
+                   "gmr_dense_proj_f32")
+    LAUNCHES += 2
+    return out
+
+
 def tc_supported(d, k, precision="tc"):
     """Shapes the tcgen05 scoring paths accept (operand tiles + ring stages must fit in shared memory)."""
     if precision == "tc_split":

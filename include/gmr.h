@@ -173,6 +173,20 @@ int gmr_rows_normalize_mix_f32(const float* x1, int64_t ld1, const float* x2, in
                                float eps, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Dense modality projection  C[M, N] = A[M, K] * W[K, N]  (fp32 in, fp32 out, fp32-level accuracy)
+ * replaces  torch.mm(image_embedding.weight, image_trans) / torch.mm(text_embedding.weight, text_trans)
+ *   GenMMRec/src/models/diffmm.py:115-127 (getImageFeats / getTextFeats, before the leaky ReLU)
+ *
+ * tcgen05.mma.kind::tf32 with both operands split as hi + lo (4 product terms) and two-level accumulation
+ * (TMEM per 128-column K chunk, fp32 registers across chunks); TMA-fed, persistent, HBM-bound on reading A once.
+ * Requires N == 64, K % 32 == 0, 16-byte aligned rows of A and C.  GMR_ERR_UNSUPPORTED otherwise (the host layer
+ * then falls back to the library GEMM, which is what the reference calls).
+ * ------------------------------------------------------------------------------------------- */
+int64_t gmr_dense_proj_workspace_bytes(int32_t K, int32_t N);
+int gmr_dense_proj_f32(const float* A, int64_t lda, int32_t M, int32_t K, const float* W, int64_t ldw, int32_t N, float* C,
+                       int64_t ldc, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Peer-memory plumbing for the fused SpMM + all-gather (CUDA IPC, one process per GPU).
  * gmr_peer_alloc allocates `bytes` of device memory suitable for export; gmr_peer_export fills a
  * 64-byte handle; another process maps it with gmr_peer_open.  The Python host exchanges the

@@ -443,3 +443,30 @@ def test_score_modes_agree_large(ops):
     for p in ("tc", "tc_split"):
         assert torch.equal(res[p][0], res["fp32"][0]), p
         assert torch.equal(res[p][1], res["fp32"][1]), p
+
+
+@pytest.mark.parametrize("m,k", [(1000, 4096), (129, 384), (128, 32), (5000, 96), (77, 1024)])
+def test_dense_proj_fp32_accuracy(ops, m, k):
+    """Split-TF32 tcgen05 projection vs an fp64 product: as accurate as a plain fp32 GEMM (and far from single-pass
+    TF32, whose error would be ~1e-3)."""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(m + k)
+    a = torch.randn(m, k, device="cuda", generator=g).clamp_(min=0)        # CNN-like non-negative features
+    a[:, ::7] *= 37.0
+    w = (torch.rand(k, 64, device="cuda", generator=g) - 0.5) * 0.06          # xavier-like
+    c = ops.dense_proj(a, w)
+    ref = a.double() @ w.double()
+    err = (c.double() - ref).abs().max().item() / ref.abs().max().item()
+    err32 = ((a @ w).double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < max(2e-6, 4 * err32), (err, err32)
+    # strided output (column slice of a wider buffer) and row tail
+    wide = torch.zeros(m, 128, device="cuda")
+    ops.dense_proj(a, w, out=wide[:, 64:])
+    assert torch.equal(wide[:, 64:], c) and float(wide[:, :64].abs().max()) == 0.0
+
+
+def test_dense_proj_unsupported_is_loud(ops):
+    a = torch.zeros(10, 48, device="cuda")
+    assert not ops.dense_proj_supported(a, torch.zeros(48, 64, device="cuda"))
+    with pytest.raises(RuntimeError):
+        ops.dense_proj(a, torch.zeros(48, 64, device="cuda"))
