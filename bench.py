@@ -239,7 +239,9 @@ def run_gpu(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    use_graph = world == 1 and not args.no_graph
+    # CUDA-graph replay of the step (with several ranks the capture holds the peer-store kernels, the second stream and
+    # the NCCL barrier all-reduces; soaked at 2, 4 and 8 ranks).  GMR_GRAPH_MULTI=0 forces eager launches there.
+    use_graph = (not args.no_graph) and (world == 1 or os.environ.get("GMR_GRAPH_MULTI", "1") == "1")
 
     def timed(fn, steps, warmup, profile=False, graph=False, sync_each=False):
         for _ in range(warmup):

@@ -442,6 +442,21 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Copy a block of rows into every peer's replica (dense all-gather by peer stores over NVLink): 128-bit loads,
+// one store per peer; grid-stride over 16-byte pieces.
+__global__ void __launch_bounds__(256)
+    rows_push_kernel(const float4* __restrict__ src, int64_t ld4, int64_t n_rows, int32_t d4, float* const* __restrict__ y_peers,
+                     int32_t n_peers, int64_t row_offset, int64_t ldy4)
+{
+    const int64_t total = n_rows * d4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / d4;
+        const int c = (int)(i - r * d4);
+        const float4 v = src[r * ld4 + c];
+        for (int p = 0; p < n_peers; ++p) reinterpret_cast<float4*>(y_peers[p])[(row_offset + r) * ldy4 + c] = v;
+    }
+}
+
 }  // namespace gmr
 
 // ---- C ABI -------------------------------------------------------------------------------------
@@ -599,6 +614,27 @@ extern "C" int gmr_rows_normalize_mix_f32(const float* x1, int64_t ld1, const fl
     const int wpb = 8;
     gmr::rows_normalize_mix_kernel<<<(unsigned)((n_rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
         x1, ld1, x2, ld2, y, ldy, out, ldo, n_rows, D, w1, w2, slope, eps);
+    GMR_LAUNCH_CHECK();
+    return GMR_OK;
+}
+
+extern "C" int gmr_rows_push_f32(const float* src, int64_t ld, int64_t n_rows, int32_t D, float* const* y_peers,
+                                 int32_t n_peers, int64_t row_offset, int64_t ldy, void* stream)
+{
+    GMR_REQUIRE(y_peers != nullptr && n_peers >= 1, "gmr_rows_push_f32: need at least one destination");
+    GMR_REQUIRE(n_rows >= 0 && D >= 4 && D % 4 == 0 && ld % 4 == 0 && ldy % 4 == 0 && row_offset >= 0,
+                "gmr_rows_push_f32: D, ld and ldy must be multiples of 4 (got D=%d ld=%lld ldy=%lld)", D, (long long)ld,
+                (long long)ldy);
+    if (n_rows == 0) return GMR_OK;
+    GMR_REQUIRE(src != nullptr && (uintptr_t)src % 16 == 0, "gmr_rows_push_f32: src must be 16-byte aligned");
+    const int64_t total = n_rows * (D / 4);
+    int64_t blocks = (total + 255) / 256;
+    // NVLink-bound: a small grid saturates the links and leaves the SMs to the SpMMs running beside it on the
+    // compute stream (a full-size grid slowed those by 2x while waiting on store back-pressure)
+    const int64_t cap = (int64_t)gmr::sm_count() / 2;
+    if (blocks > cap) blocks = cap;
+    gmr::rows_push_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(src), ld / 4, n_rows, D / 4, y_peers, n_peers, row_offset, ldy / 4);
     GMR_LAUNCH_CHECK();
     return GMR_OK;
 }

@@ -122,6 +122,18 @@ def spmm_push(a, x, ptr_table, n_peers, row_offset, ldy, alpha=1.0):
     ops.LAUNCHES += 1 + (1 if need > 0 else 0)
 
 
+def rows_push(x, ptr_table, n_peers, row_offset, ldy):
+    """Dense all-gather by peer stores: the rows of ``x`` land at row ``row_offset`` of every peer's replica."""
+    lib = _lib.load()
+    xp, ldx = ops._rows(x, "x")
+    with torch.cuda.device(x.device):
+        ev = ops._prof_begin()
+        _lib.check(lib.gmr_rows_push_f32(xp, ldx, int(x.shape[0]), int(x.shape[1]), C.c_void_p(ptr_table.data_ptr()),
+                                         int(n_peers), int(row_offset), int(ldy), ops._stream()), "gmr_rows_push_f32")
+        ops._prof_end("rows_push", ev, bytes=4.0 * x.shape[0] * x.shape[1] * n_peers, peers=int(n_peers))
+    ops.LAUNCHES += 1
+
+
 def stream_barrier(token):
     """Cross-rank barrier ordered on the current CUDA stream (no host synchronisation): a 1-element NCCL
     all-reduce completes only after every rank has enqueued -- and therefore finished -- the work before it."""
@@ -152,17 +164,20 @@ class ShardedDiffMM(object):
     """Row-sharded ``forward_MM`` of a DiffMM model replica (parameters replicated, graphs sharded).
 
     Rank g owns users [u0, u1) and items [i0, i1).  Same regrouped dataflow as the single-GPU
-    ``DiffMM._forward_mm_fused``, cut by output rows:
+    ``DiffMM._forward_mm_fused``, cut by output rows.  Every operand a later SpMM needs in full
+    lives in a buffer replicated on all ranks and is filled by each rank storing its row block into every replica over
+    NVLink peer memory -- from the SpMM epilogue itself where the block comes out of an SpMM (``spmm_push``), from a
+    copy kernel otherwise (``rows_push``) -- followed by a stream-ordered barrier:
 
-        [Z | Z + I0][i-block]   sharded projections + gmr_rows_normalize_mix     NCCL all-gather -> Xi [I, 2d]
-        Hz_g      = R_hat[g] . Z            K1 PUSH into every peer's Hz [U, d]   (fused all-gather over NVLink)
-        modal_u,g = R_hat[g] . (Z + I0)     K1, local
-        modal_i,g = R_hat'[g] . (U0 + Hz)   K1, local
-        modal_g  += lambda (w0 A_v + w1 A_t)[g] . [U0; I0]                        K1, local, in place
-        modal     = NCCL all-gather of the row blocks;   L_g = A[g] . modal       K1, local
-        E_g       = modal_g + L_g + ris_lambda n(modal_g)
+        [Z | Z + I0][i-block]   sharded projections + gmr_rows_normalize_mix      rows_push -> Xi [I, 2d]
+        P_u, P_i                modality-graph terms lambda (w0 A_v + w1 A_t)[g] E0, K1, local, while Xi travels
+        [Hz | modal_u]_g = [0 | P_u] + R_hat[g] . Xi                              K1, ONE 128-wide local pass
+        xu_g      = U0_g + Hz_g             rows_push -> Xu [U, d];   modal_u,g rows_push -> modal [N, d]
+        modal_i,g = P_i + R_hat'[g] . Xu    K1, local, while modal_u travels;     rows_push -> modal
+        L_g       = A[g] . modal            K1, local (item rows first: the final item block travels during the user rows)
+        E_g       = modal_g + L_g + ris_lambda n(modal_g);  item block rows_push -> final item table [I, d]
 
-    and the result rows (users of the block, items of the block) are returned with the block bounds.
+    and the result rows (users of the block, full item table) are returned with the block bounds.
     """
 
     def __init__(self, model, group=None):
@@ -182,29 +197,62 @@ class ShardedDiffMM(object):
         self.u0, self.u1, self.i0, self.i1 = self.ub[g], self.ub[g + 1], self.ib[g], self.ib[g + 1]
         self.r_ui = adj.ui.row_block(self.u0, self.u1)       # [U_g, I]
         self.r_iu = adj.iu.row_block(self.i0, self.i1)       # [I_g, U]
-        self.hz = PeerBuffer(nu, d, self.dev, group)         # R_hat Z, gathered by the push SpMM
-        self.token = torch.zeros(1, device=self.dev)
-        self._graphs_version = None
+        # replicated operands, each filled by every rank pushing its row block
+        self.xi_all = PeerBuffer(ni, 2 * d, self.dev, group)  # [Z | Z + I0],  Z = w0 n(F_v) + w1 n(F_t)
+        self.xu_all = PeerBuffer(nu, d, self.dev, group)      # U0 + R_hat Z
+        self.modal_all = PeerBuffer(nu + ni, d, self.dev, group)   # modal, then each further layer output
+        self.items_all = PeerBuffer(ni, d, self.dev, group)  # final item table
+        self.token = torch.zeros(1, device=self.dev)      # barrier token of the compute stream
+        self.token_c = torch.zeros(1, device=self.dev)    # barrier token of the communication stream
+        self.comm = torch.cuda.Stream(device=self.dev)
+        ug, ig = self.u1 - self.u0, self.i1 - self.i0
+        mk = lambda r: torch.empty((r, d), dtype=torch.float32, device=self.dev)
+        # row-block work buffers that cross streams (allocated once: the caching allocator never sees them freed)
+        self.buf = {"xi_local": torch.empty((ig, 2 * d), dtype=torch.float32, device=self.dev),
+                    "yu": torch.empty((ug, 2 * d), dtype=torch.float32, device=self.dev),
+                    "modal_i": mk(ig), "xu_g": mk(ug), "acc_i": mk(ig)}
+        self._adj_ref = None
         self._mix_sig = None
 
     def _graph_blocks(self, w0, w1):
         m = self.model
         nu = m.n_users
         full = m.norm_adj.full
-        if self._graphs_version is not full:
+        if self._adj_ref is not full:
             self.adj_u = full.row_block(self.u0, self.u1)
             self.adj_i = full.row_block(nu + self.i0, nu + self.i1)
-            self._graphs_version = full
+            self._adj_ref = full
         mix = m._modal_mix_graph(m.image_UI_matrix, m.text_UI_matrix, w0, w1)
         sig = (w0, w1, m.ris_adj_lambda, id(mix))
         if self._mix_sig != sig:
             self.mix_u = mix.row_block(self.u0, self.u1)
             self.mix_i = mix.row_block(nu + self.i0, nu + self.i1)
             self._mix_sig = sig
+            self._mix_ref = mix
         return self
 
+    def _on_comm(self, after, fn):
+        """Run ``fn`` on the communication stream once ``after`` (an event of the compute stream) has fired; returns
+        an event of the communication stream that fires when fn's work -- including the cross-rank barrier it ends
+        with, if any -- is done."""
+        self.comm.wait_event(after)
+        with torch.cuda.stream(self.comm):
+            fn()
+            ev = torch.cuda.Event()
+            ev.record()
+        return ev
+
+    @staticmethod
+    def _mark():
+        ev = torch.cuda.Event()
+        ev.record()
+        return ev
+
     @torch.no_grad()
-    def forward_MM(self):
+    def forward_MM(self, push_items=False):
+        """Row blocks (users, items) of the propagated embeddings.  Peer stores run on a second stream and overlap
+        the SpMMs that do not depend on them: the modality-graph terms are computed while Xi travels, modal_u travels
+        during the item-row SpMM, the final item block during the user-row layer."""
         m = self.model
         nu, ni, d = m.n_users, m.n_items, m.latdim
         u0, u1, i0, i1 = self.u0, self.u1, self.i0, self.i1
@@ -212,51 +260,93 @@ class ShardedDiffMM(object):
         self._graph_blocks(w0, w1)
         e0 = m._packed_e0()
         U0, I0 = e0[:nu], e0[nu:]
-        usz = [self.ub[g + 1] - self.ub[g] for g in range(self.world)]
-        isz = [self.ib[g + 1] - self.ib[g] for g in range(self.world)]
-        # 1. sharded projections -> gathered Xi = [Z | Z + I0]
-        pv = torch.mm(m.v_feat[i0:i1], m.image_trans.detach())
-        pt = torch.mm(m.t_feat[i0:i1], m.text_trans.detach())
-        xi_local = ops.rows_normalize_mix(pv, pt, w0, w1, y=I0[i0:i1], slope=m.leakyrelu.negative_slope)
-        xi = all_gather_rows(xi_local, isz, self.group)
-        # 2. user rows: R_hat Z pushed to every replica of Hz (fused all-gather); modal_u stays local
-        spmm_push(self.r_ui, xi[:, :d], self.hz.ptr_table, self.world, u0, d)
-        modal_u = ops.spmm_raw(self.r_ui, xi[:, d:])
-        stream_barrier(self.token)
-        # 3. item rows: modal_i = R_hat' (U0 + R_hat Z)
-        xu = torch.add(U0, self.hz.tensor)
-        modal_i = ops.spmm_raw(self.r_iu, xu)
-        stream_barrier(self.token)   # nobody may overwrite Hz (next call) before every rank has read it
-        # 4. modality graphs, accumulated in place
-        ops.spmm_raw(self.mix_u, e0, out=modal_u, beta=1.0)
-        ops.spmm_raw(self.mix_i, e0, out=modal_i, beta=1.0)
-        # 5. GCN layers over the full adjacency
-        acc_u = acc_i = None
-        last_u, last_i = modal_u, modal_i
-        for layer in range(m.gnn_layer):
-            full = torch.cat([all_gather_rows(last_u, usz, self.group), all_gather_rows(last_i, isz, self.group)])
-            last_u, last_i = ops.spmm_raw(self.adj_u, full), ops.spmm_raw(self.adj_i, full)
-            if layer == 0:
-                acc_u = ops.rows_axpby_norm(modal_u, last_u, modal_u, a=1.0, b=1.0, c=m.ris_lambda)
-                acc_i = ops.rows_axpby_norm(modal_i, last_i, modal_i, a=1.0, b=1.0, c=m.ris_lambda)
-            else:
-                ops.rows_axpby_norm(acc_u, last_u, None, a=1.0, b=1.0, out=acc_u)
-                ops.rows_axpby_norm(acc_i, last_i, None, a=1.0, b=1.0, out=acc_i)
-        if acc_u is None:
+        W = self.world
+        cur = torch.cuda.current_stream()
+        stream_barrier(self.token)       # step fence: every rank has finished reading the replicated buffers
+        # 1. sharded projections -> [Z | Z + I0] of the item block -> every replica (comm stream): the owner adds
+        #    its I0 rows, so no rank ever runs a full-size elementwise pass
+        pv = m._project(m.v_feat[i0:i1], m.image_trans.detach())
+        pt = m._project(m.t_feat[i0:i1], m.text_trans.detach())
+        xi_local = ops.rows_normalize_mix(pv, pt, w0, w1, y=I0[i0:i1], slope=m.leakyrelu.negative_slope,
+                                          out=self.buf["xi_local"])
+
+        def push_xi():
+            rows_push(xi_local, self.xi_all.ptr_table, W, i0, 2 * d)
+            stream_barrier(self.token_c)
+        ev_z = self._on_comm(self._mark(), push_xi)
+        #    meanwhile: the modality-graph terms (no remote data) seed the accumulators of the two big passes
+        yu = self.buf["yu"]                                      # [U_g, 2d] = R_hat Z | modal_u
+        yu[:, :d].zero_()
+        ops.spmm_raw(self.mix_u, e0, out=yu[:, d:])
+        modal_i = ops.spmm_raw(self.mix_i, e0, out=self.buf["modal_i"])
+        # 2. user rows: ONE 128-wide pass  yu += R_hat[g] [Z | Z + I0];  xu_g = U0_g + R_hat Z -> every replica of xu
+        cur.wait_event(ev_z)
+        ops.spmm_raw(self.r_ui, self.xi_all.tensor, out=yu, beta=1.0)
+        modal_u = yu[:, d:]
+        xu_g = ops.rows_axpby_norm(U0[u0:u1], yu[:, :d], None, a=1.0, b=1.0, out=self.buf["xu_g"])
+
+        def push_xu():
+            rows_push(xu_g, self.xu_all.ptr_table, W, u0, d)
+            stream_barrier(self.token_c)
+        ev_hz = self._on_comm(self._mark(), push_xu)
+        ev_mu = self._on_comm(self._mark(), lambda: rows_push(modal_u, self.modal_all.ptr_table, W, u0, d))
+        # 3. item rows: modal_i += R_hat'[g] (U0 + R_hat Z)   (modal_u travels meanwhile)
+        cur.wait_event(ev_hz)
+        ops.spmm_raw(self.r_iu, self.xu_all.tensor, out=modal_i, beta=1.0)
+        if m.gnn_layer == 0:
+            cur.wait_event(ev_mu)
             acc_u = ops.rows_axpby_norm(modal_u, None, modal_u, a=1.0, c=m.ris_lambda)
             acc_i = ops.rows_axpby_norm(modal_i, None, modal_i, a=1.0, c=m.ris_lambda)
+            return self._finish(acc_u, acc_i, push_items)
+
+        def push_mi():
+            rows_push(modal_i, self.modal_all.ptr_table, W, nu + i0, d)
+            stream_barrier(self.token_c)
+        ev_m = self._on_comm(self._mark(), push_mi)
+        # 4. first GCN layer: item rows first, so that the final item block can travel during the user rows
+        cur.wait_event(ev_m)
+        full = self.modal_all.tensor
+        last_i = ops.spmm_raw(self.adj_i, full)
+        acc_i = ops.rows_axpby_norm(modal_i, last_i, modal_i, a=1.0, b=1.0, c=m.ris_lambda, out=self.buf["acc_i"])
+        ev_items = None
+        if m.gnn_layer == 1 and push_items:
+            def push_items_fn():
+                rows_push(acc_i, self.items_all.ptr_table, W, i0, d)
+                stream_barrier(self.token_c)
+            ev_items = self._on_comm(self._mark(), push_items_fn)
+        last_u = ops.spmm_raw(self.adj_u, full)
+        acc_u = ops.rows_axpby_norm(modal_u, last_u, modal_u, a=1.0, b=1.0, c=m.ris_lambda)
+        # 5. further layers (not overlapped): gather the previous layer output, multiply, accumulate
+        for _ in range(m.gnn_layer - 1):
+            stream_barrier(self.token)   # every rank has read `full` before it is overwritten
+            rows_push(last_u, self.modal_all.ptr_table, W, u0, d)
+            rows_push(last_i, self.modal_all.ptr_table, W, nu + i0, d)
+            stream_barrier(self.token)
+            last_u, last_i = ops.spmm_raw(self.adj_u, full), ops.spmm_raw(self.adj_i, full)
+            ops.rows_axpby_norm(acc_u, last_u, None, a=1.0, b=1.0, out=acc_u)
+            ops.rows_axpby_norm(acc_i, last_i, None, a=1.0, b=1.0, out=acc_i)
+        return self._finish(acc_u, acc_i, push_items, ev_items)
+
+    def _finish(self, acc_u, acc_i, push_items, ev_items=None):
+        cur = torch.cuda.current_stream()
+        if push_items and ev_items is None:
+            rows_push(acc_i, self.items_all.ptr_table, self.world, self.i0, self.model.latdim)
+            stream_barrier(self.token)
+        if ev_items is not None:
+            cur.wait_event(ev_items)
+        cur.wait_stream(self.comm)   # join: nothing of this call is left on the communication stream
         return acc_u, acc_i
 
     def close(self):
         """Release the peer-mapped buffers (CUDA IPC mappings of the other ranks' replicas)."""
-        self.hz.close()
+        for buf in (self.xi_all, self.xu_all, self.modal_all, self.items_all):
+            buf.close()
 
     @torch.no_grad()
     def eval_factors(self):
-        """(user rows of this rank's block, full item table): the item block is all-gathered."""
-        out_u, out_i = self.forward_MM()
-        isz = [self.ib[g + 1] - self.ib[g] for g in range(self.world)]
-        return out_u, all_gather_rows(out_i, isz, self.group)
+        """(user rows of this rank's block, full item table): every rank stores its item block into every replica."""
+        out_u, _ = self.forward_MM(push_items=True)
+        return out_u, self.items_all.tensor
 
 
 def shard_eval_by_user_block(loader, u0, u1):

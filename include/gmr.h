@@ -83,6 +83,12 @@ int gmr_spmm_csr_f32_push(const gmr_spmm_plan_t* plan, const int32_t* rowptr, co
                           int64_t ldy, int32_t D, float alpha, void* workspace, int64_t workspace_bytes,
                           void* stream);
 
+/* Dense all-gather of a row block by peer stores: rows [0, n_rows) of `src` (leading dimension ld) are copied to
+ * y_peers[p] + (row_offset + r) * ldy for every p (own replica included).  D, ld, ldy multiples of 4, 16-byte
+ * aligned buffers.  The caller synchronises the ranks (a stream-ordered barrier) before anyone reads. */
+int gmr_rows_push_f32(const float* src, int64_t ld, int64_t n_rows, int32_t D, float* const* y_peers, int32_t n_peers,
+                      int64_t row_offset, int64_t ldy, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K2  fused score + train-history mask + top-K (the [B, I] score matrix is never written)
  * replaces  torch.matmul(u_e[user], i_e.T)  ->  scores[mask] = -1e10  ->  torch.topk(scores, K)
