@@ -204,46 +204,50 @@ struct PruneResult {
 // too little, L is recomputed from ALL keys (exact K-th lb).
 //
 // Key layout here: (ordered s~) << 32 | sweep position p  (NOT the item id: nb[] and perm[] are indexed by p).
-template <int NPL>
-__device__ __noinline__ PruneResult screen_prune(uint64_t* __restrict__ s_row, int cnt, int n_checked, float ce, float ab,
+template <int NPL, int NACT>
+__device__ __noinline__ PruneResult screen_prune_impl(uint64_t* __restrict__ s_row, int cnt, int n_checked, float ce, float ab,
                                                  const float* __restrict__ nb, const int32_t* __restrict__ perm,
                                                  const int32_t* __restrict__ mask_items, int64_t mlo, int64_t mhi, int K,
                                                  int lane, unsigned long long* stats)
 {
+    // NACT <= NPL key registers per lane are live (cnt <= 32 * NACT): a half-full buffer -- the state at every
+    // checkpoint after phase 0 -- costs half the loads, searches and compare-exchanges
     constexpr int CAP = 32 * NPL;
     constexpr int M = NPL / 2;
-    uint64_t k[NPL];
-    uint32_t lb[NPL];  // order-preserving bits; 0 = empty
-    float ub[NPL];
+    static_assert(NACT == NPL || NACT == M, "NACT is NPL or NPL / 2");
+    uint64_t k[NACT];
+    uint32_t lb[NACT];  // order-preserving bits; 0 = empty
+    float ub[NACT];
 #pragma unroll
-    for (int r = 0; r < NPL; ++r) {
+    for (int r = 0; r < NACT; ++r) {
         const int i = r * 32 + lane;
         k[r] = (i < cnt) ? s_row[i] : 0ull;
     }
     if (mlo < mhi) {
         // NPL binary searches in lock-step over the row's ascending train-history list: every step issues NPL
         // independent loads (branch-free lower bound), so the chain costs log2(len) latencies, not NPL * log2(len)
-        int32_t id[NPL];
-        int64_t base[NPL];
+        int32_t id[NACT];
+        int32_t base[NACT];   // offsets from mlo
 #pragma unroll
-        for (int r = 0; r < NPL; ++r) {
+        for (int r = 0; r < NACT; ++r) {
             const int i = r * 32 + lane;
             id[r] = (k[r] != 0ull && i >= n_checked) ? perm[(uint32_t)k[r]] : -1;  // -1: nothing to look up
-            base[r] = mlo;
+            base[r] = 0;
         }
-        int64_t len = mhi - mlo;
+        const int32_t* __restrict__ ml = mask_items + mlo;
+        int32_t len = (int32_t)(mhi - mlo);
         while (len > 1) {
-            const int64_t half = len >> 1;
+            const int32_t half = len >> 1;
 #pragma unroll
-            for (int r = 0; r < NPL; ++r) base[r] += (mask_items[base[r] + half - 1] < id[r]) ? half : 0;
+            for (int r = 0; r < NACT; ++r) base[r] += (ml[base[r] + half - 1] < id[r]) ? half : 0;
             len -= half;
         }
 #pragma unroll
-        for (int r = 0; r < NPL; ++r)
-            if (id[r] >= 0 && mask_items[base[r]] == id[r]) k[r] = 0ull;
+        for (int r = 0; r < NACT; ++r)
+            if (id[r] >= 0 && ml[base[r]] == id[r]) k[r] = 0ull;
     }
 #pragma unroll
-    for (int r = 0; r < NPL; ++r) {
+    for (int r = 0; r < NACT; ++r) {
         lb[r] = 0u;
         ub[r] = -INFINITY;
         if (k[r] != 0ull) {
@@ -258,7 +262,7 @@ __device__ __noinline__ PruneResult screen_prune(uint64_t* __restrict__ s_row, i
 #pragma unroll
     for (int m = 0; m < M; ++m) pool[m] = 0u;
 #pragma unroll
-    for (int r = 0; r < NPL; ++r) {
+    for (int r = 0; r < NACT; ++r) {
         uint32_t x = lb[r];
 #pragma unroll
         for (int m = 0; m < M; ++m) {
@@ -278,30 +282,30 @@ __device__ __noinline__ PruneResult screen_prune(uint64_t* __restrict__ s_row, i
     float L = (lk != 0u) ? ordered_to_f32(lk) : -INFINITY;
     int total = 0;
 #pragma unroll
-    for (int r = 0; r < NPL; ++r) total += __popc(__ballot_sync(0xffffffffu, lb[r] != 0u && ub[r] >= L));
+    for (int r = 0; r < NACT; ++r) total += __popc(__ballot_sync(0xffffffffu, lb[r] != 0u && ub[r] >= L));
     bool exact = false;
     if (total > CAP * 5 / 8) {
         // exact K-th largest lb over all keys
         exact = true;
-        uint32_t all[NPL];
+        uint32_t all[NACT];
 #pragma unroll
-        for (int r = 0; r < NPL; ++r) all[r] = lb[r];
-        warp_bitonic_sort_desc<NPL, uint32_t>(all, lane);
+        for (int r = 0; r < NACT; ++r) all[r] = lb[r];
+        warp_bitonic_sort_desc<NACT, uint32_t>(all, lane);
         lk = 0u;
 #pragma unroll
-        for (int r = 0; r < NPL; ++r) {
+        for (int r = 0; r < NACT; ++r) {
             const uint32_t cand = __shfl_sync(0xffffffffu, all[r], kth & 31);
             if (r == (kth >> 5)) lk = cand;
         }
         L = (lk != 0u) ? ordered_to_f32(lk) : -INFINITY;
         total = 0;
 #pragma unroll
-        for (int r = 0; r < NPL; ++r) total += __popc(__ballot_sync(0xffffffffu, lb[r] != 0u && ub[r] >= L));
+        for (int r = 0; r < NACT; ++r) total += __popc(__ballot_sync(0xffffffffu, lb[r] != 0u && ub[r] >= L));
     }
     // compact survivors in place (order is irrelevant)
     int mine = 0;
 #pragma unroll
-    for (int r = 0; r < NPL; ++r) mine += (lb[r] != 0u && ub[r] >= L) ? 1 : 0;
+    for (int r = 0; r < NACT; ++r) mine += (lb[r] != 0u && ub[r] >= L) ? 1 : 0;
     int pre = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -311,7 +315,7 @@ __device__ __noinline__ PruneResult screen_prune(uint64_t* __restrict__ s_row, i
     int pos = pre - mine;
     __syncwarp();
 #pragma unroll
-    for (int r = 0; r < NPL; ++r)
+    for (int r = 0; r < NACT; ++r)
         if (lb[r] != 0u && ub[r] >= L) s_row[pos++] = k[r];
     __syncwarp();
     if (stats && lane == 0) atomicAdd(&stats[exact ? 3 : 2], 1ull);
@@ -319,6 +323,17 @@ __device__ __noinline__ PruneResult screen_prune(uint64_t* __restrict__ s_row, i
     res.cnt = (total > CAP - 64) ? -1 : total;
     res.lbK = (total > CAP - 64) ? INFINITY : L;
     return res;
+}
+
+template <int NPL>
+__device__ __forceinline__ PruneResult screen_prune(uint64_t* __restrict__ s_row, int cnt, int n_checked, float ce, float ab,
+                                                    const float* __restrict__ nb, const int32_t* __restrict__ perm,
+                                                    const int32_t* __restrict__ mask_items, int64_t mlo, int64_t mhi, int K,
+                                                    int lane, unsigned long long* stats)
+{
+    if (cnt <= 16 * NPL && K <= 16 * NPL)   // warp-uniform
+        return screen_prune_impl<NPL, NPL / 2>(s_row, cnt, n_checked, ce, ab, nb, perm, mask_items, mlo, mhi, K, lane, stats);
+    return screen_prune_impl<NPL, NPL>(s_row, cnt, n_checked, ce, ab, nb, perm, mask_items, mlo, mhi, K, lane, stats);
 }
 
 // ---- 3. the fused kernel ----------------------------------------------------------------------------
