@@ -7,11 +7,11 @@
 // (8.2 GB at the 1M-user shape = 1.26 ms) but runs at CUDA-core speed through cuBLAS (4.4 ms, 60 TFLOP/s fp32 SIMT).
 //
 // Scheme: split-TF32 with fp32-level accuracy.  Every fp32 operand x is written as hi + lo with hi = x rounded to
-// TF32's 11 significant bits and lo = x - hi (exact in fp32, then cut to TF32 as well); the product sums the four
-// terms hi.hi + hi.lo + lo.hi + lo.lo on tcgen05.mma.kind::tf32, so the only error is the truncation of lo
-// (2^-22 relative per operand) plus fp32 accumulation.  Accumulation is two-level: TMEM holds the sum of one K chunk
-// (128 columns = 64 MMAs), the epilogue warps add the chunk sums into fp32 registers with IEEE adds, so the
-// tensor-core accumulator never carries more than 64 partial products.
+// TF32's 11 significant bits and lo = x - hi (exact in fp32, then cut to TF32 as well); the product sums the three
+// terms hi.hi + hi.lo + lo.hi on tcgen05.mma.kind::tf32 (3xTF32), so the error is the truncation of lo plus the
+// dropped lo.lo term (each <= 2^-22 relative per product, below the fp32 rounding of the sum) plus fp32 accumulation.  Accumulation is two-level: TMEM holds the sum of one K chunk
+// (128 columns = 48 MMAs), the epilogue warps add the chunk sums into fp32 registers with IEEE adds, so the
+// tensor-core accumulator never carries more than 48 partial products.
 //
 // Measured (1M-user shape, M = 500k, K = 4096): 2.9 ms = 3.1 TB/s of A, against 4.4 ms for cuBLAS fp32 and a 1.26 ms
 // HBM floor.  The limiter is shared-memory bandwidth, not HBM or the tensor pipe: with N = 64 every MMA re-reads its
@@ -20,11 +20,13 @@
 // bought nothing; the next step is the A-operand-in-TMEM form of tcgen05.mma (splitter writes hi / lo with tcgen05.st).
 //
 // One persistent CTA per SM, 128 rows of A per tile, warp-specialised:
-//   warp 0     TMA producer: per K atom (32 fp32 = 128 B per row) the A tile (16 KB) and the hi / lo atoms of W^T
-//              (8 KB each, L2-resident) into a 4-stage ring, 128-byte swizzle
-//   warps 2-5  splitter: rewrite the landed A atom in place as hi and write lo next to it (same swizzled layout, so the
-//              pass is purely elementwise), fence.proxy.async, arrive
-//   warp 1     MMA issuer: 16 tcgen05.mma (M 128, N 64, K 8) per atom into a double-buffered TMEM accumulator
+//   warp 0     TMA producer: per K atom (32 fp32 = 128 B per row) the raw A tile (16 KB) and the hi / lo atoms of W^T
+//              (8 KB each, L2-resident) into a 6-stage ring, 128-byte swizzle
+//   warps 2-5  splitter (thread = row): read the row's 32 floats from the swizzled tile, split, and store hi / lo as 32
+//              TMEM columns each (tcgen05.st) -- the A operand lives in TENSOR MEMORY, so the 16 MMAs of an atom do not
+//              re-read 64 KB of A from shared memory (shared-memory bandwidth was the limiter of the first version)
+//   warp 1     MMA issuer: 16 tcgen05.mma (M 128, N 64, K 8; A from TMEM, W from shared memory) per atom into a
+//              double-buffered TMEM accumulator
 //   warps 6-9  epilogue: tcgen05.ld the chunk sums, add into 64 fp32 registers per row, store the row at tile end
 #include <cuda.h>
 
@@ -35,12 +37,12 @@ namespace gmr {
 
 constexpr int kPM = 128;          // rows of A per tile (UMMA M)
 constexpr int kPN = 64;           // output columns (UMMA N)
-constexpr int kPStages = 4;
+constexpr int kPStages = 6;
 constexpr int kPChunkAtoms = 4;   // K atoms per TMEM accumulation chunk (K = 128)
 constexpr int kPThreads = 320;
 constexpr uint32_t kPAtomA = kPM * 128;   // 16 KB
 constexpr uint32_t kPAtomW = kPN * 128;   // 8 KB
-constexpr uint32_t kPStageBytes = 2 * kPAtomA + 2 * kPAtomW;  // A hi, A lo, W hi, W lo = 48 KB
+constexpr uint32_t kPStageBytes = kPAtomA + 2 * kPAtomW;      // raw A, W hi, W lo = 32 KB
 
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo)
 {
@@ -82,6 +84,36 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n)
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc)
+{
+    // A operand read from tensor memory (lane = row, one 32-bit column per K element), B from shared memory
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tc_st_32x32(uint32_t taddr, const uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+        "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+        "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tc_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// TMEM columns: [0, 128) two accumulators, [128, 256) two A stages of (hi 32 | lo 32) columns
+constexpr uint32_t kPTmemCols = 256;
+constexpr uint32_t kPTmemA = 2 * kPN;
+
 __global__ void __launch_bounds__(kPThreads, 1)
     dense_proj_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_wh,
                       const __grid_constant__ CUtensorMap map_wl, float* __restrict__ C, int64_t ldc, int32_t M, int32_t K)
@@ -89,12 +121,13 @@ __global__ void __launch_bounds__(kPThreads, 1)
     extern __shared__ uint8_t smem_dyn[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kPStages * kPStageBytes);
-    uint64_t* full = bars;                        // [kPStages] TMA landed
-    uint64_t* split = bars + kPStages;            // [kPStages] hi / lo written (128 arrivals)
-    uint64_t* empty = bars + 2 * kPStages;        // [kPStages] MMAs retired
-    uint64_t* acc_full = bars + 3 * kPStages;     // [2]
-    uint64_t* acc_empty = bars + 3 * kPStages + 2;  // [2] (128 arrivals)
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 3 * kPStages + 4);
+    uint64_t* full = bars;                        // [kPStages] TMA landed (raw A atom + W hi / lo atoms)
+    uint64_t* empty = bars + kPStages;            // [kPStages] MMAs that read the stage's W atoms retired
+    uint64_t* split = bars + 2 * kPStages;        // [2] A hi / lo of the TMEM stage written (128 arrivals)
+    uint64_t* a_free = bars + 2 * kPStages + 2;   // [2] MMAs that read the TMEM stage retired
+    uint64_t* acc_full = bars + 2 * kPStages + 4;     // [2]
+    uint64_t* acc_empty = bars + 2 * kPStages + 6;    // [2] (128 arrivals)
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPStages + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = (M + kPM - 1) / kPM;
@@ -104,10 +137,11 @@ __global__ void __launch_bounds__(kPThreads, 1)
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < kPStages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&split[s], 128);
             mbar_init(&empty[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
+            mbar_init(&split[s], 128);
+            mbar_init(&a_free[s], 1);
             mbar_init(&acc_full[s], 1);
             mbar_init(&acc_empty[s], 128);
         }
@@ -118,7 +152,7 @@ __global__ void __launch_bounds__(kPThreads, 1)
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
-                     "r"(2 * kPN)
+                     "r"(kPTmemCols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -138,13 +172,13 @@ __global__ void __launch_bounds__(kPThreads, 1)
                     uint8_t* st = smem + (size_t)s * kPStageBytes;
                     mbar_expect_tx(&full[s], kPAtomA + 2 * kPAtomW);
                     tma_load_2d(st, &map_a, &full[s], k * 32, tile * kPM);
-                    tma_load_2d(st + 2 * kPAtomA, &map_wh, &full[s], k * 32, 0);
-                    tma_load_2d(st + 2 * kPAtomA + kPAtomW, &map_wl, &full[s], k * 32, 0);
+                    tma_load_2d(st + kPAtomA, &map_wh, &full[s], k * 32, 0);
+                    tma_load_2d(st + kPAtomA + kPAtomW, &map_wl, &full[s], k * 32, 0);
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
+        // ===== MMA issuer: A (hi / lo) from tensor memory, W^T (hi / lo) from shared memory =====
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_tf32(kPM, kPN);
             uint32_t g = 0, c = 0;
@@ -157,49 +191,57 @@ __global__ void __launch_bounds__(kPThreads, 1)
                     const int k_end = min(n_atoms, (ch + 1) * kPChunkAtoms);
                     for (int k = ch * kPChunkAtoms; k < k_end; ++k, ++g) {
                         const uint32_t s = g % kPStages, ph = (g / kPStages) & 1u;
-                        mbar_wait(&split[s], ph);
+                        const uint32_t ta = g & 1u, tph = (g >> 1) & 1u;
+                        mbar_wait(&full[s], ph);       // W atoms in shared memory
+                        mbar_wait(&split[ta], tph);    // A hi / lo in tensor memory
                         tc_fence_after();
-                        const uint32_t a_hi = smem_u32(smem + (size_t)s * kPStageBytes);
-                        const uint32_t a_lo = a_hi + kPAtomA, w_hi = a_hi + 2 * kPAtomA, w_lo = w_hi + kPAtomW;
+                        const uint32_t w_hi = smem_u32(smem + (size_t)s * kPStageBytes + kPAtomA), w_lo = w_hi + kPAtomW;
+                        const uint32_t a_hi = tmem_base + kPTmemA + ta * 64, a_lo = a_hi + 32;
                         const bool first = (k == ch * kPChunkAtoms);
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {  // 4 x (K = 8 fp32 = 32 B) per 128-byte swizzle row
+                        for (int kk = 0; kk < 4; ++kk) {  // 4 x (K = 8): 8 TMEM columns of A, 32 B of each W row
                             const uint32_t o = kk * 32;
-                            tc_mma_tf32(d_tmem, umma_desc_sw128(a_lo + o), umma_desc_sw128(w_lo + o), idesc, (first && kk == 0) ? 0u : 1u);
-                            tc_mma_tf32(d_tmem, umma_desc_sw128(a_lo + o), umma_desc_sw128(w_hi + o), idesc, 1u);
-                            tc_mma_tf32(d_tmem, umma_desc_sw128(a_hi + o), umma_desc_sw128(w_lo + o), idesc, 1u);
-                            tc_mma_tf32(d_tmem, umma_desc_sw128(a_hi + o), umma_desc_sw128(w_hi + o), idesc, 1u);
+                            // lo.lo (<= 2^-22 of the product, below the fp32 rounding of the sum) is not issued
+                            tc_mma_tf32_ts(d_tmem, a_lo + kk * 8, umma_desc_sw128(w_hi + o), idesc, (first && kk == 0) ? 0u : 1u);
+                            tc_mma_tf32_ts(d_tmem, a_hi + kk * 8, umma_desc_sw128(w_lo + o), idesc, 1u);
+                            tc_mma_tf32_ts(d_tmem, a_hi + kk * 8, umma_desc_sw128(w_hi + o), idesc, 1u);
                         }
                         tc_commit(&empty[s]);
+                        tc_commit(&a_free[ta]);
                     }
                     tc_commit(&acc_full[buf]);
                 }
             }
         }
     } else if (warp < 6) {
-        // ===== splitter: A atom -> (hi in place, lo next to it); layout-agnostic elementwise pass =====
-        const int t = threadIdx.x - 64;  // 0..127
+        // ===== splitter: thread = row.  raw A atom (shared memory, 128-byte swizzle) -> hi / lo columns in TMEM =====
+        const int q = warp & 3;                     // TMEM lane quarter this warp may touch
+        const int row = q * 32 + lane;
         uint32_t g = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             for (int k = 0; k < n_atoms; ++k, ++g) {
                 const uint32_t s = g % kPStages, ph = (g / kPStages) & 1u;
+                const uint32_t ta = g & 1u, tph = (g >> 1) & 1u;
                 mbar_wait(&full[s], ph);
-                float4* hi4 = reinterpret_cast<float4*>(smem + (size_t)s * kPStageBytes);
-                float4* lo4 = reinterpret_cast<float4*>(smem + (size_t)s * kPStageBytes + kPAtomA);
+                const uint8_t* rowp = smem + (size_t)s * kPStageBytes + (size_t)row * 128;
+                uint32_t hi[32], lo[32];
 #pragma unroll
-                for (int j = 0; j < (int)(kPAtomA / 16 / 128); ++j) {  // 8 x 16-byte pieces per thread
-                    const int i = j * 128 + t;
-                    const float4 x = hi4[i];
-                    float4 h, l;
-                    split_tf32(x.x, h.x, l.x);
-                    split_tf32(x.y, h.y, l.y);
-                    split_tf32(x.z, h.z, l.z);
-                    split_tf32(x.w, h.w, l.w);
-                    hi4[i] = h;
-                    lo4[i] = l;
+                for (int j = 0; j < 8; ++j) {       // logical 16-byte chunk j sits at physical chunk j ^ (row & 7)
+                    const float4 x = *reinterpret_cast<const float4*>(rowp + ((j ^ (row & 7)) << 4));
+                    float h, l;
+                    split_tf32(x.x, h, l); hi[4 * j + 0] = __float_as_uint(h); lo[4 * j + 0] = __float_as_uint(l);
+                    split_tf32(x.y, h, l); hi[4 * j + 1] = __float_as_uint(h); lo[4 * j + 1] = __float_as_uint(l);
+                    split_tf32(x.z, h, l); hi[4 * j + 2] = __float_as_uint(h); lo[4 * j + 2] = __float_as_uint(l);
+                    split_tf32(x.w, h, l); hi[4 * j + 3] = __float_as_uint(h); lo[4 * j + 3] = __float_as_uint(l);
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
-                mbar_arrive(&split[s]);
+                mbar_wait(&a_free[ta], tph ^ 1);    // the MMAs that read this TMEM stage last have retired
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + kPTmemA + ta * 64;
+                tc_st_32x32(taddr, hi);
+                tc_st_32x32(taddr + 32, lo);
+                tc_st_wait();
+                tc_fence_before();
+                mbar_arrive(&split[ta]);
             }
         }
     } else {
@@ -240,7 +282,7 @@ __global__ void __launch_bounds__(kPThreads, 1)
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * kPN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kPTmemCols) : "memory");
     }
 }
 
@@ -317,7 +359,7 @@ extern "C" int gmr_dense_proj_f32(const float* A, int64_t lda, int32_t M, int32_
         set_error("gmr_dense_proj_f32: cuTensorMapEncodeTiled unavailable or failed");
         return GMR_ERR_CUDA;
     }
-    const size_t smem = (size_t)kPStages * kPStageBytes + (3 * kPStages + 6) * sizeof(uint64_t) + 1024;
+    const size_t smem = (size_t)kPStages * kPStageBytes + (2 * kPStages + 10) * sizeof(uint64_t) + 1024;
     GMR_CHECK_CUDA(cudaFuncSetAttribute(dense_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int n_tiles = (M + kPM - 1) / kPM;
     const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
