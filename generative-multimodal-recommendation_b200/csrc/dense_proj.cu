@@ -13,11 +13,11 @@
 // (128 columns = 48 MMAs), the epilogue warps add the chunk sums into fp32 registers with IEEE adds, so the
 // tensor-core accumulator never carries more than 48 partial products.
 //
-// Measured (1M-user shape, M = 500k, K = 4096): 2.9 ms = 3.1 TB/s of A, against 4.4 ms for cuBLAS fp32 and a 1.26 ms
-// HBM floor.  The limiter is shared-memory bandwidth, not HBM or the tensor pipe: with N = 64 every MMA re-reads its
-// 4 KB A slice and 2 KB W slice from shared memory (96 KB per K atom for the 16 MMAs + 80 KB of TMA / splitter
-// traffic = 1,375 cycles at 128 B/clk against 520 cycles of MMA time).  A deeper HBM prefetch ring was tried and
-// bought nothing; the next step is the A-operand-in-TMEM form of tcgen05.mma (splitter writes hi / lo with tcgen05.st).
+// Measured (1M-user shape, M = 500k, K = 4096 + 384): 2.33 ms for both projections = 3.9 TB/s of feature bytes (60 % of
+// the measured HBM copy peak), against 4.8 ms for cuBLAS fp32 SIMT and a 1.4 ms HBM floor; ncu: tensor pipe 35 % active,
+// DRAM 48 %.  History: A in shared memory with 4 terms was shared-memory-bandwidth bound (every MMA re-read its 4 KB A
+// slice: 2.9 ms); moving A to tensor memory gave 2.7 ms, dropping lo.lo 2.33 ms.  Tried without effect: 8 splitter warps
+// + 4 TMEM A stages, a deeper HBM ring, L2 prefetch of the adjacent K atoms (DRAM page locality).
 //
 // One persistent CTA per SM, 128 rows of A per tile, warp-specialised:
 //   warp 0     TMA producer: per K atom (32 fp32 = 128 B per row) the raw A tile (16 KB) and the hi / lo atoms of W^T
