@@ -113,7 +113,12 @@ __global__ void __launch_bounds__(kWarps * 32, (ITER == 1) ? 4 : 2)
     constexpr int UNROLL = (ITER >= 2) ? 2 : 4;  // steps whose gathers are issued back to back
     constexpr int GROUP = NPS * UNROLL;          // nonzeros per unrolled batch
     constexpr int STAGE = 256;  // (col, val) pairs staged per pass: a whole chunk at the default size
-    __shared__ int2 stage[kWarps][STAGE];
+    // double-buffered staging of the CSR stream: the NEXT virtual row's (col, val) pairs are copied global -> shared
+    // with cp.async while the current row's gathers are in flight, and the row after that has its pointers loaded,
+    // so a row's critical path is its gathers only (it used to be pointer load -> CSR load -> gathers -> store:
+    // two of the four memory latencies of a 50-nonzero row)
+    __shared__ int scol[kWarps][2][STAGE];
+    __shared__ float sval[kWarps][2][STAGE];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sub = lane % LANES, grp = lane / LANES;
@@ -125,56 +130,99 @@ __global__ void __launch_bounds__(kWarps * 32, (ITER == 1) ? 4 : 2)
     for (int it = 0; it < ITER; ++it) colok[it] = EXACT || (vcol0 + it * LANES < DV);
 
     const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+    auto issue_stage = [&](int buf, int base, int n) {  // n <= STAGE entries, one cp.async group per call
+        for (int k = lane; k < n; k += 32) {
+            asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(&scol[warp][buf][k])),
+                         "l"(col + base + k), "l"(pol_stream)
+                         : "memory");
+            asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(&sval[warp][buf][k])),
+                         "l"(val + base + k), "l"(pol_stream)
+                         : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     // Persistent warps: every warp walks virtual rows v, v + W, v + 2W, ... (W = warps in the grid).  Row lengths are
     // power-law distributed; with one virtual row per warp a CTA stays resident until its longest row is done and the
     // SM runs at a third of its warp slots (ncu: 32 % warps active).  Striding keeps every slot busy until the tail.
     const int64_t n_warps_grid = (int64_t)gridDim.x * kWarps;
-    for (int64_t v = (int64_t)blockIdx.x * kWarps + warp; v < n_vrows; v += n_warps_grid) {
-    const int begin = vptr[v], end = vptr[v + 1];
-    const int dst = IDENT ? (int)v : vrow[v];
+    int64_t v = (int64_t)blockIdx.x * kWarps + warp;
+    if (v >= n_vrows) return;  // whole warp leaves together; only __syncwarp below
+    int begin = vptr[v], end = vptr[v + 1];
+    int dst = IDENT ? (int)v : vrow[v];
+    issue_stage(0, begin, min(STAGE, end - begin));
+    int64_t vn = v + n_warps_grid;
+    int begin1 = 0, end1 = 0, dst1 = 0;
+    if (vn < n_vrows) {
+        begin1 = vptr[vn];
+        end1 = vptr[vn + 1];
+        dst1 = IDENT ? (int)vn : vrow[vn];
+    }
+    int buf = 0;
+    while (true) {
+    const bool has_next = vn < n_vrows;
+    if (has_next)
+        issue_stage(buf ^ 1, begin1, min(STAGE, end1 - begin1));
+    else
+        asm volatile("cp.async.commit_group;" ::: "memory");  // keeps the group count uniform
+    const int64_t vnn = vn + n_warps_grid;
+    int begin2 = 0, end2 = 0, dst2 = 0;
+    if (vnn < n_vrows) {
+        begin2 = vptr[vnn];
+        end2 = vptr[vnn + 1];
+        dst2 = IDENT ? (int)vnn : vrow[vnn];
+    }
     Vec acc[ITER];
 #pragma unroll
     for (int it = 0; it < ITER; ++it) acc[it] = Ops::zero();
 
     auto row_ptr = [&](int c) -> const Vec* {
-        if (OFF32) return Xl + (uint32_t)c;  // c is already col * ldv
+        if (OFF32) return Xl + (uint32_t)c * ldv;
         return reinterpret_cast<const Vec*>(X + (int64_t)c * ldx) + vcol0;
     };
-    const int2* my_stage = stage[warp];
+    const int* my_col = scol[warp][buf];
+    const float* my_val = sval[warp][buf];
     // one batch = GROUP nonzeros: UNROLL gathers per lane
-    auto load_group = [&](int g, int2 (&cw)[UNROLL], Vec (&xv)[UNROLL][ITER]) {
-#pragma unroll
-        for (int q = 0; q < UNROLL; ++q) cw[q] = my_stage[g * GROUP + q * NPS + grp];
+    auto load_group = [&](int g, float (&cw)[UNROLL], Vec (&xv)[UNROLL][ITER]) {
+        int cc[UNROLL];
 #pragma unroll
         for (int q = 0; q < UNROLL; ++q) {
-            const Vec* xr = row_ptr(cw[q].x);
+            cc[q] = my_col[g * GROUP + q * NPS + grp];
+            cw[q] = my_val[g * GROUP + q * NPS + grp];
+        }
+#pragma unroll
+        for (int q = 0; q < UNROLL; ++q) {
+            const Vec* xr = row_ptr(cc[q]);
 #pragma unroll
             for (int it = 0; it < ITER; ++it)
                 xv[q][it] = colok[it] ? Ops::gather(xr + it * LANES, pol_keep) : Ops::zero();
         }
     };
-    auto fma_group = [&](const int2 (&cw)[UNROLL], const Vec (&xv)[UNROLL][ITER]) {
+    auto fma_group = [&](const float (&cw)[UNROLL], const Vec (&xv)[UNROLL][ITER]) {
 #pragma unroll
         for (int q = 0; q < UNROLL; ++q)
 #pragma unroll
-            for (int it = 0; it < ITER; ++it) Ops::fma(acc[it], __int_as_float(cw[q].y), xv[q][it]);
+            for (int it = 0; it < ITER; ++it) Ops::fma(acc[it], cw[q], xv[q][it]);
     };
 
+    asm volatile("cp.async.wait_group 1;" ::: "memory");  // this row's first STAGE entries have landed (own copies)
+    __syncwarp();                                         // ... and every other lane's
     for (int base = begin; base < end; base += STAGE) {
         const int n = min(STAGE, end - base);
-        __syncwarp();
-        for (int k = lane; k < n; k += 32) {  // coalesced CSR stream -> shared memory
-            int c = ld_stream_s32(col + base + k, pol_stream);
-            const float w = ld_stream_f32(val + base + k, pol_stream);
-            if (OFF32) c = (int)((uint32_t)c * ldv);
-            stage[warp][k] = make_int2(c, __float_as_int(w));
+        if (base != begin) {  // rows longer than one stage (custom chunk sizes only): plain synchronous staging
+            __syncwarp();
+            for (int k = lane; k < n; k += 32) {
+                scol[warp][buf][k] = ld_stream_s32(col + base + k, pol_stream);
+                sval[warp][buf][k] = ld_stream_f32(val + base + k, pol_stream);
+            }
+            __syncwarp();
         }
-        __syncwarp();
         // software pipeline over full batches: the gathers of batch g+1 are issued before the FMAs of
         // batch g, so every warp keeps UNROLL..2*UNROLL independent 128-bit gathers in flight
         const int ng = n / GROUP;
         if (ng > 0) {
-            int2 cwA[UNROLL], cwB[UNROLL];
+            float cwA[UNROLL], cwB[UNROLL];
             Vec xA[UNROLL][ITER], xB[UNROLL][ITER];
             load_group(0, cwA, xA);
             int g = 0;
@@ -188,20 +236,20 @@ __global__ void __launch_bounds__(kWarps * 32, (ITER == 1) ? 4 : 2)
             }
         }
         for (int e = ng * GROUP + grp; e < n; e += NPS) {  // ragged tail of the row
-            const int2 cw = my_stage[e];
-            const Vec* xr = row_ptr(cw.x);
+            const Vec* xr = row_ptr(my_col[e]);
+            const float w = my_val[e];
 #pragma unroll
             for (int it = 0; it < ITER; ++it)
-                if (colok[it]) Ops::fma(acc[it], __int_as_float(cw.y), Ops::gather(xr + it * LANES, pol_keep));
+                if (colok[it]) Ops::fma(acc[it], w, Ops::gather(xr + it * LANES, pol_keep));
         }
     }
+    __syncwarp();  // every lane is done with this stage buffer before the row after next is copied into it
 
     if (NPS == 2) {
 #pragma unroll
         for (int it = 0; it < ITER; ++it) acc[it] = Ops::xor_add(acc[it], 16);
     }
-    if (grp != 0) continue;
-
+    if (grp == 0) {
 #pragma unroll
     for (int it = 0; it < ITER; ++it) {
         const int vc = vcol0 + it * LANES;
@@ -221,6 +269,11 @@ __global__ void __launch_bounds__(kWarps * 32, (ITER == 1) ? 4 : 2)
             *y = (beta == 0.f) ? Ops::scale(alpha, acc[it]) : Ops::axpby(alpha, acc[it], beta, *y);
         }
     }
+    }
+    if (!has_next) break;
+    v = vn; begin = begin1; end = end1; dst = dst1;
+    vn = vnn; begin1 = begin2; end1 = end2; dst1 = dst2;
+    buf ^= 1;
     }  // persistent loop over virtual rows
 }
 
