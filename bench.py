@@ -370,7 +370,7 @@ def run_gpu(args):
             "metric": "full_sort_eval_users_per_s", "value": n_eval_total / step_ms * 1e3, "unit": "users/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD_NAMES[args.workload], "model": "DiffMM", "n_users": wl.n_users,
+            "config": {"workload": WORKLOAD_NAMES[args.workload], "propagation": "DiffMM forward_MM (GenMMRec/src/models/diffmm.py:129-169)", "n_users": wl.n_users,
                        "n_items": wl.n_items, "nnz_train": wl.nnz_train, "eval_users": n_eval_total, "topk": k,
                        "embedding_size": cfg["embedding_size"], "n_layers": cfg["n_layers"],
                        "score_precision": args.precision,
@@ -486,7 +486,7 @@ def run_reference(args):
         "n_gpus": world, "steps": args.steps, "steps_run": steps, "warmup": args.warmup, "warmup_run": warm + 1,
         "ms_per_step": base["seconds_per_batch"] * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAMES[args.workload], "model": "DiffMM", "n_users": wl.n_users,
+        "config": {"workload": WORKLOAD_NAMES[args.workload], "propagation": "DiffMM forward_MM (GenMMRec/src/models/diffmm.py:129-169)", "n_users": wl.n_users,
                    "n_items": wl.n_items, "nnz_train": wl.nnz_train, "eval_users": wl.n_eval_users, "topk": k,
                    "embedding_size": wl.config["embedding_size"], "n_layers": wl.config["n_layers"]},
         "cpu_baseline": base,
