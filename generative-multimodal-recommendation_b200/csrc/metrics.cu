@@ -45,6 +45,10 @@ __global__ void __launch_bounds__(kMU)
     const double n = (double)(hi - lo);
     const int lim = (int)min((int64_t)K, hi - lo);
     double c = 0.0, dcg = 0.0, idcg = 0.0, sp = 0.0;
+    // c / n, dcg / idcg, sp / min(pos + 1, lim) as of the last change (0 / 0 = NaN for a user without ground truth, as
+    // the literal expressions give)
+    const double q0 = (hi > lo) ? 0.0 : nan("");
+    double q_recall = q0, q_ndcg = q0, q_map = q0;
 
     for (int k0 = 0; k0 < K; k0 += kKC) {
         const int kc = min(kKC, K - k0);
@@ -62,15 +66,28 @@ __global__ void __launch_bounds__(kMU)
             tile[t][k] = h;
             double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
             if (valid) {
+                // fp64 divides are the cost of this kernel (5 per user and position when written literally): the hit
+                // count c changes on a hit only, the ideal DCG only while pos < lim, so quotients are refreshed when
+                // their operands change and reused otherwise -- same expressions, same results
                 const double disc = c_discount[pos];
-                c += (double)h;
-                dcg += (double)h * disc;
-                if (pos < lim) idcg += disc;
-                sp += (double)h * (c / (double)(pos + 1));
-                v0 = c / n;
-                v1 = dcg / idcg;
-                v2 = c / (double)(pos + 1);
-                v3 = sp / (double)min(pos + 1, lim);
+                if (h) {
+                    c += 1.0;
+                    dcg += disc;
+                    sp += c / (double)(pos + 1);
+                    q_recall = c / n;
+                }
+                if (pos < lim) {
+                    idcg += disc;
+                    q_ndcg = dcg / idcg;
+                    q_map = sp / (double)(pos + 1);
+                } else if (h) {
+                    q_ndcg = dcg / idcg;
+                    q_map = sp / (double)lim;
+                }
+                v0 = q_recall;
+                v1 = q_ndcg;
+                v2 = (c != 0.0) ? c / (double)(pos + 1) : 0.0;
+                v3 = q_map;
             }
             v0 = warp_sum(v0);
             v1 = warp_sum(v1);

@@ -94,27 +94,33 @@ __global__ void __launch_bounds__(256)
     if (lane == 0 && m > 0.f) atomicMax(out_bits, __float_as_uint(m));
 }
 
-// item norms in scaled units (rounded up: they feed BOUNDS) as sortable bits + the identity permutation
+// item norms (UNSCALED, rounded up: they feed BOUNDS) as sortable bits + the identity permutation, and the global
+// absmax that fixes the power-of-two item scale -- one pass over the item table.  The sort order does not depend on the
+// scale; prep_items_kernel multiplies the sorted norms by it (exact: a power of two).
 __global__ void __launch_bounds__(256)
-    item_norms_kernel(const float* __restrict__ E, int64_t lde, int32_t n_rows, int32_t D,
-                      const uint32_t* __restrict__ gmax_bits, uint32_t* __restrict__ norm_bits, int32_t* __restrict__ ident)
+    item_norms_kernel(const float* __restrict__ E, int64_t lde, int32_t n_rows, int32_t D, uint32_t* __restrict__ gmax_bits,
+                      uint32_t* __restrict__ norm_bits, int32_t* __restrict__ ident)
 {
     const int lane = threadIdx.x & 31;
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= n_rows) return;
-    const float s = pow2_scale_for(__uint_as_float(*gmax_bits));
-    float ss = 0.f;
+    float ss = 0.f, m = 0.f;
     for (int d = lane; d < D; d += 32) {
-        const float x = E[r * lde + d] * s;
+        const float x = E[r * lde + d];
         ss = fmaf(x, x, ss);
+        m = fmaxf(m, fabsf(x));
     }
 #pragma unroll
-    for (int m = 16; m > 0; m >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, m);
+    for (int k = 16; k > 0; k >>= 1) {
+        ss += __shfl_xor_sync(0xffffffffu, ss, k);
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, k));
+    }
     if (lane == 0) {
         float nrm = sqrtf(ss) * 1.000001f;
         if (!(nrm < INFINITY)) nrm = 3.0e38f;  // NaN / inf rows sort first and never allow an early stop
         norm_bits[r] = __float_as_uint(nrm);
         ident[r] = (int32_t)r;
+        if (m > 0.f && m < INFINITY) atomicMax(gmax_bits, __float_as_uint(m));
     }
 }
 
@@ -132,9 +138,13 @@ __global__ void __launch_bounds__(256)
     __half* o = out + p * (int64_t)D;
     const float* src = (p < n_rows) ? E + (int64_t)perm[p] * lde : nullptr;
     for (int d = lane; d < D; d += 32) o[d] = __float2half_rn(src ? src[d] * s : 0.f);
-    if (lane == 0 && p >= n_rows) {
-        perm[p] = -1;
-        nb[p] = 0.f;
+    if (lane == 0) {
+        if (p >= n_rows) {
+            perm[p] = -1;
+            nb[p] = 0.f;
+        } else {
+            nb[p] *= s;   // sorted unscaled norm -> scaled units
+        }
     }
 }
 
@@ -417,7 +427,7 @@ __device__ __forceinline__ void final_sort_write(uint64_t (&ek)[NSORT], int lane
 // the oracle (bit-exact).  The user row is read from shared memory; the item row comes from the CTA's
 // shared-memory copy of the `n_hot` highest-norm rows when p < n_hot (where nearly every candidate of a
 // popularity-skewed catalogue lives: 32 lanes gathering 32 different 256-byte rows from global memory cost 32 L1
-// wavefronts per load instruction, from padded shared memory ~6), otherwise from global memory with the 64 floats of
+// wavefronts per load instruction, from padded shared memory ~6), otherwise from global memory with the 32 floats of
 // each block loaded up front (one memory latency per block instead of one per element).
 __device__ __forceinline__ uint64_t exact_key(const ScrArgs& a, const float* __restrict__ u_sm, uint32_t p,
                                               const float* __restrict__ e_hot, int n_hot, int hot_pitch)
@@ -440,12 +450,12 @@ __device__ __forceinline__ uint64_t exact_key(const ScrArgs& a, const float* __r
     const float* e = a.Ei + (int64_t)item * a.lde_i;
     if (a.vec4) {
         const float4* e4 = reinterpret_cast<const float4*>(e);
-        for (int d0 = 0; d0 < a.D / 4; d0 += 16) {
-            float4 ev[16];
+        for (int d0 = 0; d0 < a.D / 4; d0 += 8) {
+            float4 ev[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) ev[j] = __ldg(e4 + d0 + j);
+            for (int j = 0; j < 8; ++j) ev[j] = __ldg(e4 + d0 + j);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < 8; ++j) {
                 const float4 uv = u4[d0 + j];
                 s = fmaf(uv.x, ev[j].x, s);
                 s = fmaf(uv.y, ev[j].y, s);
@@ -809,7 +819,7 @@ __global__ void __launch_bounds__(kScrThreads, 1)
 // Applies the train-history mask to the row's first candidates, computes L and the number of item tiles the
 // row still needs; the maximum over each 256-user group decides whether phase 1 touches the group at all.
 template <int NPL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (NPL == 8) ? 4 : ((NPL == 16) ? 3 : 2))
     score_screen_checkpoint_kernel(ScrArgs a)
 {
     constexpr int CAP = 32 * NPL;
@@ -846,7 +856,7 @@ __global__ void __launch_bounds__(256)
 // (score desc, id asc), write the top K; undecidable rows are queued for the fp32 kernel.  Each CTA first copies the
 // `n_hot` highest-norm item rows (sweep positions 0 .. n_hot-1) into padded shared memory.
 template <int NPL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (NPL == 8) ? 3 : 2)
     score_screen_finalize_kernel(ScrArgs a, int n_hot)
 {
     constexpr int CAP = 32 * NPL;
@@ -1055,17 +1065,13 @@ int score_topk_screen_launch(const float* Eu, int64_t lde_u, const int64_t* user
 
     GMR_CHECK_CUDA(cudaMemsetAsync(misc, 0, 256, st));
     const int wpb = 8;
-    {
+    if (bias != nullptr) {
         const int64_t warps = ((int64_t)I + 3) / 4;  // ~4 rows per warp
         int grid = (int)((warps + wpb - 1) / wpb);
         if (grid > 16 * sm_count()) grid = 16 * sm_count();
         if (grid < 1) grid = 1;
-        absmax_kernel<<<grid, wpb * 32, 0, st>>>(Ei, lde_i, I, D, misc);
+        absmax_kernel<<<grid, wpb * 32, 0, st>>>(bias, 1, I, 1, misc + 3);
         GMR_LAUNCH_CHECK();
-        if (bias != nullptr) {
-            absmax_kernel<<<grid, wpb * 32, 0, st>>>(bias, 1, I, 1, misc + 3);
-            GMR_LAUNCH_CHECK();
-        }
     }
     item_norms_kernel<<<(I + wpb - 1) / wpb, wpb * 32, 0, st>>>(Ei, lde_i, I, D, misc, nb_raw, ident);
     GMR_LAUNCH_CHECK();

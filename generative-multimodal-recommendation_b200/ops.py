@@ -337,8 +337,9 @@ def score_mask_topk(eu, ei, k, users=None, bias=None, mask_rowptr=None, mask_ite
                                                _ptr(ws), need, _stream()), "gmr_score_mask_topk_f32")
         _prof_end("score_topk", ev, flops=2.0 * b * i * d, users=b, items=i, d=d, k=k, precision=precision)
     # own kernels only (the cub radix sort of the item norms is library code and not counted):
-    # tc: absmax + item norms + 2 operand-prep kernels + fused kernel + fp32 redo; tc_split: 2 split kernels + fused + redo
-    LAUNCHES += {_lib.GMR_SCORE_FP32: 1, _lib.GMR_SCORE_TC: 6 + (1 if bias is not None else 0), _lib.GMR_SCORE_TC_SPLIT: 4}[mode]
+    # tc: item norms + 2 operand-prep kernels + 2 sweeps + checkpoint + finalize + fp32 redo (+ bias absmax);
+    # tc_split: 2 split kernels + fused + redo
+    LAUNCHES += {_lib.GMR_SCORE_FP32: 1, _lib.GMR_SCORE_TC: 8 + (1 if bias is not None else 0), _lib.GMR_SCORE_TC_SPLIT: 4}[mode]
     global _last_score_call
     _last_score_call = (ws, b, i, d, k, mode)
     return ids, scores
