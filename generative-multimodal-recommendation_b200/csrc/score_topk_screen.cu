@@ -312,21 +312,20 @@ __device__ __noinline__ PruneResult screen_prune_impl(uint64_t* __restrict__ s_r
 #pragma unroll
         for (int r = 0; r < NACT; ++r) total += __popc(__ballot_sync(0xffffffffu, lb[r] != 0u && ub[r] >= L));
     }
-    // compact survivors in place (order is irrelevant)
-    int mine = 0;
-#pragma unroll
-    for (int r = 0; r < NACT; ++r) mine += (lb[r] != 0u && ub[r] >= L) ? 1 : 0;
-    int pre = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, pre, o);
-        if (lane >= o) pre += y;
-    }
-    int pos = pre - mine;
+    // compact survivors in place, keeping their slot order (= sweep order for keys appended by the sweep): neighbouring
+    // slots then hold neighbouring sweep positions, and the finalisation's 32 lanes read 32 rows of the staged item
+    // block whose shared-memory bank groups (position mod 8) differ.  (A lane-major compaction put positions 32 apart
+    // into neighbouring slots: 3x the shared-memory wavefronts, the limiter of the finalize kernel.)
+    const uint32_t lt = (1u << lane) - 1u;
+    int base = 0;
     __syncwarp();
 #pragma unroll
-    for (int r = 0; r < NACT; ++r)
-        if (lb[r] != 0u && ub[r] >= L) s_row[pos++] = k[r];
+    for (int r = 0; r < NACT; ++r) {
+        const bool keep = lb[r] != 0u && ub[r] >= L;
+        const unsigned kb = __ballot_sync(0xffffffffu, keep);
+        if (keep) s_row[base + __popc(kb & lt)] = k[r];
+        base += __popc(kb);
+    }
     __syncwarp();
     if (stats && lane == 0) atomicAdd(&stats[exact ? 3 : 2], 1ull);
     PruneResult res;
