@@ -242,15 +242,23 @@ def run_gpu(args):
     # CUDA-graph replay of the step (with several ranks the capture holds the peer-store kernels, the second stream and
     # the NCCL barrier all-reduces; soaked at 2, 4 and 8 ranks).  GMR_GRAPH_MULTI=0 forces eager launches there.
     use_graph = (not args.no_graph) and (world == 1 or os.environ.get("GMR_GRAPH_MULTI", "1") == "1")
+    graph_state = {"failed": False}
 
     def timed(fn, steps, warmup, profile=False, graph=False, sync_each=False):
         for _ in range(warmup):
             fn()
         barrier()
-        run = trainer.graphed(fn) if graph else fn
+        run = fn
         if graph:
-            for _ in range(2):
-                run()
+            try:
+                run = trainer.graphed(fn)
+                for _ in range(2):
+                    run()
+            except Exception as e:  # capture refused (e.g. an NCCL build without graph support): time eager launches
+                sys.stderr.write("[bench] CUDA-graph capture failed (%r); timing eager launches instead\n" % (e,))
+                graph_state["failed"] = True
+                run = fn
+                torch.cuda.synchronize()
             barrier()
         if profile:
             ops.PROFILE = []
@@ -374,7 +382,7 @@ def run_gpu(args):
                        "n_items": wl.n_items, "nnz_train": wl.nnz_train, "eval_users": n_eval_total, "topk": k,
                        "embedding_size": cfg["embedding_size"], "n_layers": cfg["n_layers"],
                        "score_precision": args.precision,
-                       "launch": "CUDA graph replay of the whole step" if use_graph else "eager launches",
+                       "launch": "CUDA graph replay of the whole step" if (use_graph and not graph_state["failed"]) else "eager launches",
                        "parallelism": ("row-sharded propagation (push-SpMM all-gather) + user-block sharded eval, x%d" % world)
                        if world > 1 else "single GPU",
                        "l2": ("L2 flushed between timed steps (operands fit the %d MB L2)" % (l2_bytes >> 20)) if need_flush

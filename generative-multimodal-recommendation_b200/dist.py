@@ -349,6 +349,106 @@ class ShardedDiffMM(object):
         return out_u, self.items_all.tensor
 
 
+class ShardedGCNChain(object):
+    """Row-sharded LightGCN-style propagation  c = sum_g w_g * mean_{l=0..L} G^l E0  over one or more N x N graphs:
+    ``LightGCN.forward`` (GenMMRec/src/models/lightgcn.py:115-127, one graph) and the content embedding GenRecV1
+    scores with (``user_item_GCN`` x 2, GenMMRec/src/models/genrecv1.py:255-264,335-341, the normalised adjacency and
+    the generated-edge graph).  Rank g owns users [u0, u1) and items [i0, i1) of every graph; a layer output that the
+    next layer needs in full is stored by every rank into every replica (``rows_push``) behind a stream-ordered
+    barrier; with one layer (the shipped GenRecV1 / LightGCN settings use 1-4) the first product reads the replicated
+    parameters directly.  The propagated item block is pushed into the replicated item table for scoring."""
+
+    def __init__(self, model, graphs_fn, weights_fn, embeddings_fn, n_layers, group=None):
+        """graphs_fn() -> list of GraphCSR [N, N]; weights_fn() -> list of floats; embeddings_fn() -> (U0, I0)."""
+        import torch.distributed as dist
+
+        self.model, self.group = model, group
+        self.graphs_fn, self.weights_fn, self.embeddings_fn, self.n_layers = graphs_fn, weights_fn, embeddings_fn, n_layers
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.dev = model.device
+        nu, ni = model.n_users, model.n_items
+        u0_, i0_ = embeddings_fn()
+        self.d = int(u0_.shape[1])
+        first = graphs_fn()[0]
+        counts = (first.rowptr[1:] - first.rowptr[:-1]).to(torch.int64).cpu()
+        rp_u = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(counts[:nu], 0)])
+        rp_i = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(counts[nu:], 0)])
+        self.ub, self.ib = nnz_balanced_bounds(rp_u, self.world), nnz_balanced_bounds(rp_i, self.world)
+        g = self.rank
+        self.u0, self.u1, self.i0, self.i1 = self.ub[g], self.ub[g + 1], self.ib[g], self.ib[g + 1]
+        self.layer_all = PeerBuffer(nu + ni, self.d, self.dev, group)
+        self.items_all = PeerBuffer(ni, self.d, self.dev, group)
+        self.token = torch.zeros(1, device=self.dev)
+        self._blocks = {}
+
+    def _row_blocks(self, graph):
+        key = id(graph)
+        hit = self._blocks.get(key)
+        if hit is None or hit[0] is not graph:
+            nu = self.model.n_users
+            hit = (graph, graph.row_block(self.u0, self.u1), graph.row_block(nu + self.i0, nu + self.i1))
+            self._blocks[key] = hit
+        return hit[1], hit[2]
+
+    @torch.no_grad()
+    def forward(self):
+        nu, d, W = self.model.n_users, self.d, self.world
+        U0, I0 = self.embeddings_fn()
+        e0 = torch.cat([U0.detach(), I0.detach()])
+        out_u = out_i = None
+        for graph, w in zip(self.graphs_fn(), self.weights_fn()):
+            g_u, g_i = self._row_blocks(graph)
+            acc_u, acc_i = e0[self.u0:self.u1].clone(), e0[nu + self.i0:nu + self.i1].clone()
+            full = e0
+            for layer in range(self.n_layers):
+                last_u, last_i = ops.spmm_raw(g_u, full), ops.spmm_raw(g_i, full)
+                acc_u += last_u
+                acc_i += last_i
+                if layer + 1 < self.n_layers:
+                    stream_barrier(self.token)   # every rank is done reading the previous layer
+                    rows_push(last_u, self.layer_all.ptr_table, W, self.u0, d)
+                    rows_push(last_i, self.layer_all.ptr_table, W, nu + self.i0, d)
+                    stream_barrier(self.token)
+                    full = self.layer_all.tensor
+            scale = float(w) / float(self.n_layers + 1)
+            out_u = acc_u * scale if out_u is None else out_u + acc_u * scale
+            out_i = acc_i * scale if out_i is None else out_i + acc_i * scale
+            stream_barrier(self.token)           # the next graph's chain reuses the layer buffer
+        return out_u, out_i
+
+    @torch.no_grad()
+    def eval_factors(self):
+        out_u, out_i = self.forward()
+        rows_push(out_i.contiguous(), self.items_all.ptr_table, self.world, self.i0, self.d)
+        stream_barrier(self.token)
+        return out_u, self.items_all.tensor
+
+    def close(self):
+        self.layer_all.close()
+        self.items_all.close()
+
+
+def sharded_genrecv1(model, group=None):
+    """Row-sharded evaluation propagation of a GenRecV1 replica (its ``propagate()``: the content embedding)."""
+    import torch.nn.functional as F
+
+    def weights():
+        w = F.softmax(torch.stack([model.origin_weight.detach(), model.generation_weight.detach()]).flatten(), dim=0)
+        return [float(x) for x in w.tolist()]
+
+    from .models._common import as_graph
+    return ShardedGCNChain(model, lambda: [as_graph(model.norm_adj), as_graph(model.image_UI_matrix)], weights,
+                           lambda: (model.user_embedding.weight, model.item_id_embedding.weight), model.n_layers, group)
+
+
+def sharded_lightgcn(model, group=None):
+    """Row-sharded ``LightGCN.forward`` (mean of the layer outputs over the normalised adjacency)."""
+    from .models._common import as_graph
+    return ShardedGCNChain(model, lambda: [as_graph(model.norm_adj_matrix)], lambda: [1.0],
+                           lambda: (model.embedding_dict["user_emb"], model.embedding_dict["item_emb"]), model.n_layers, group)
+
+
 def shard_eval_by_user_block(loader, u0, u1):
     """The eval users whose id falls in [u0, u1), in loader order, with their mask / ground-truth CSR
     slices and user ids rebased to the block (so they index the rank-local user rows)."""

@@ -20,6 +20,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--shape", default="baby")
+    ap.add_argument("--model", default="DiffMM", choices=["DiffMM", "GenRecV1", "LightGCN"])
+    ap.add_argument("--layers", type=int, default=2)
     args = ap.parse_args()
     from genmmrec_b200 import dist as gd, ops
     from genmmrec_b200.common.trainer import Trainer
@@ -30,15 +32,15 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    wl = Workload("DiffMM", args.shape, dev, overrides={"n_layers": 2})
+    wl = Workload(args.model, args.shape, dev, overrides={"n_layers": args.layers})
     model = wl.model
     trainer = Trainer(wl.config, model)
     k = max(wl.config["topk"])
     with torch.no_grad():
-        ue, ie = model.forward_MM(model.norm_adj, model.image_UI_matrix, model.text_UI_matrix)
+        ue, ie = model.propagate()
         ids_ref, _ = trainer.topk_all(wl.valid)
         sums_ref, _ = trainer.evaluator.metric_sums(ids_ref, wl.valid)
-        sh = gd.ShardedDiffMM(model)
+        sh = {"DiffMM": gd.ShardedDiffMM, "GenRecV1": gd.sharded_genrecv1, "LightGCN": gd.sharded_lightgcn}[args.model](model)
         for _ in range(2):  # twice: buffers are reused across calls
             su, items = sh.eval_factors()
         part = gd.shard_eval_by_user_block(wl.valid, sh.u0, sh.u1)
