@@ -188,6 +188,20 @@ def test_rows_axpby_norm(ops):
     out = ops.rows_axpby_norm(x, y, z, a=1.0, b=0.3, c=0.5)
     ref = x + 0.3 * y + 0.5 * torch.nn.functional.normalize(z)
     assert rel(out.cpu().numpy(), ref.double().cpu().numpy()) < 1e-6
+    # D = 64 vector path: odd row count, x a column slice of a wider buffer, z aliasing x, y absent, in-place output
+    wide = torch.from_numpy(rng.standard_normal((501, 128)).astype(np.float32)).cuda()
+    xs = wide[:, 64:]
+    ref2 = xs + 0.25 * torch.nn.functional.normalize(xs)
+    out2 = ops.rows_axpby_norm(xs, None, xs, a=1.0, c=0.25)
+    assert rel(out2.cpu().numpy(), ref2.double().cpu().numpy()) < 1e-6
+    y2 = torch.from_numpy(rng.standard_normal((501, 64)).astype(np.float32)).cuda()
+    ref3 = (y2 + 2.0 * xs).clone()
+    ops.rows_axpby_norm(y2, xs, None, a=1.0, b=2.0, out=y2)
+    assert rel(y2.cpu().numpy(), ref3.double().cpu().numpy()) < 1e-6
+    # generic path (D = 96)
+    x9, z9 = (torch.from_numpy(rng.standard_normal((77, 96)).astype(np.float32)).cuda() for _ in range(2))
+    out9 = ops.rows_axpby_norm(x9, None, z9, a=0.5, c=1.0)
+    assert rel(out9.cpu().numpy(), (0.5 * x9 + torch.nn.functional.normalize(z9)).double().cpu().numpy()) < 1e-6
 
 
 def test_errors_are_loud(ops):
