@@ -105,10 +105,19 @@ __global__ void __launch_bounds__(256)
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= n_rows) return;
     float ss = 0.f, m = 0.f;
-    for (int d = lane; d < D; d += 32) {
-        const float x = E[r * lde + d];
-        ss = fmaf(x, x, ss);
-        m = fmaxf(m, fabsf(x));
+    if ((lde & 1) == 0 && ((uintptr_t)E & 7) == 0) {   // D % 64 == 0: 8-byte loads
+        const float2* e2 = reinterpret_cast<const float2*>(E + r * lde);
+        for (int d = lane; d < D / 2; d += 32) {
+            const float2 x = e2[d];
+            ss = fmaf(x.x, x.x, fmaf(x.y, x.y, ss));
+            m = fmaxf(m, fmaxf(fabsf(x.x), fabsf(x.y)));
+        }
+    } else {
+        for (int d = lane; d < D; d += 32) {
+            const float x = E[r * lde + d];
+            ss = fmaf(x, x, ss);
+            m = fmaxf(m, fabsf(x));
+        }
     }
 #pragma unroll
     for (int k = 16; k > 0; k >>= 1) {
@@ -140,7 +149,16 @@ __global__ void __launch_bounds__(256)
     const float s = pow2_scale_for(__uint_as_float(*gmax_bits));
     __half* o = out + p * (int64_t)D;
     const float* src = (p < n_rows) ? E + (int64_t)perm[p] * lde : nullptr;
-    for (int d = lane; d < D; d += 32) o[d] = __float2half_rn(src ? src[d] * s : 0.f);
+    if (src != nullptr && (lde & 1) == 0 && ((uintptr_t)E & 7) == 0) {
+        const float2* s2 = reinterpret_cast<const float2*>(src);
+        __half2* o2 = reinterpret_cast<__half2*>(o);
+        for (int d = lane; d < D / 2; d += 32) {
+            const float2 x = s2[d];
+            o2[d] = __floats2half2_rn(x.x * s, x.y * s);
+        }
+    } else {
+        for (int d = lane; d < D; d += 32) o[d] = __float2half_rn(src ? src[d] * s : 0.f);
+    }
     if (lane == 0) {
         if (p >= n_rows) {
             perm[p] = -1;
@@ -169,17 +187,42 @@ __global__ void __launch_bounds__(256)
     if (r >= n_rows_pad) return;
     __half* o = out + r * (int64_t)D;
     const float* src = (r < n_rows) ? E + (rows ? rows[r] : r) * lde : nullptr;
+    // the row stays in registers between the absmax pass and the conversion (D <= 256: 4 x float2 per lane)
+    const bool vec = src != nullptr && (lde & 1) == 0 && ((uintptr_t)E & 7) == 0 && D <= 256;
+    float2 xr[4];
     float m = 0.f;
-    if (src)
+    if (vec) {
+        const float2* s2 = reinterpret_cast<const float2*>(src);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int d = lane + 32 * j;
+            xr[j] = (d < D / 2) ? s2[d] : make_float2(0.f, 0.f);
+            m = fmaxf(m, fmaxf(fabsf(xr[j].x), fabsf(xr[j].y)));
+        }
+    } else if (src) {
         for (int d = lane; d < D; d += 32) m = fmaxf(m, fabsf(src[d]));
+    }
 #pragma unroll
     for (int k = 16; k > 0; k >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, k));
     const float su = pow2_scale_for(m);
     float ss = 0.f;
-    for (int d = lane; d < D; d += 32) {
-        const float x = src ? src[d] * su : 0.f;
-        o[d] = __float2half_rn(x);
-        ss = fmaf(x, x, ss);
+    if (vec) {
+        __half2* o2 = reinterpret_cast<__half2*>(o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int d = lane + 32 * j;
+            if (d < D / 2) {
+                const float x0 = xr[j].x * su, x1 = xr[j].y * su;
+                o2[d] = __floats2half2_rn(x0, x1);
+                ss = fmaf(x0, x0, fmaf(x1, x1, ss));
+            }
+        }
+    } else {
+        for (int d = lane; d < D; d += 32) {
+            const float x = src ? src[d] * su : 0.f;
+            o[d] = __float2half_rn(x);
+            ss = fmaf(x, x, ss);
+        }
     }
 #pragma unroll
     for (int k = 16; k > 0; k >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, k);
