@@ -140,27 +140,6 @@ class HostInputs(object):
         return self.eval_len_list
 
 
-def shard_loader(loader, rank, world):
-    """Contiguous slice of the eval users for this rank (user-block sharding)."""
-    if world == 1:
-        return loader
-
-    class Shard(object):
-        pass
-
-    n = int(loader.eval_u.numel())
-    lo, hi = n * rank // world, n * (rank + 1) // world
-    s = Shard()
-    s.eval_u = loader.eval_u[lo:hi].contiguous()
-    for ptr, items in (("mask_rowptr", "mask_items"), ("gt_rowptr", "gt_items")):
-        rp = getattr(loader, ptr)[lo:hi + 1]
-        setattr(s, items, getattr(loader, items)[int(rp[0]):int(rp[-1])].contiguous())
-        setattr(s, ptr, (rp - rp[0]).contiguous())
-    s.eval_len_list = loader.eval_len_list[lo:hi]
-    s.get_eval_len_list = lambda: s.eval_len_list
-    return s
-
-
 def run_gpu(args):
     import torch.distributed as dist
 
