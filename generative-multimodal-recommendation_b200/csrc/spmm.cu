@@ -18,6 +18,7 @@
 //     L2::evict_last: the only operand with reuse keeps the 126 MB L2.
 //
 // HBM-bound: algorithmic bytes = nnz*8 + (n_rows+1)*4 + n_cols*D*4 + n_rows*D*4.
+#include <cstdlib>
 #include <algorithm>
 #include <vector>
 
@@ -319,6 +320,101 @@ __global__ void __launch_bounds__(kWarps * 32)
     }
 }
 
+// Short-row variant (D = 64 floats, float4 lanes): one HALF-warp per virtual row, so a warp retires two rows per trip.
+// kNN modality graphs (10 neighbours per item) and the merged modal-mix graph (~5 nonzeros per row) spend the general
+// kernel's time on per-row overhead, not on gathers: a full warp per row stages 256 slots for 5 entries and leaves half
+// its gather slots empty.  Here the (col, val) pairs live in registers (one per lane, broadcast by shuffle), the next
+// row's pairs and the row after that's pointers are loaded while this row's gathers are in flight, and nothing touches
+// shared memory.  Summation order is the general kernel's (even nonzeros into one fmaf chain, odd ones into another,
+// chains added at the end), so the two kernels return bit-identical rows and the choice is a pure scheduling matter.
+template <bool IDENT>
+__global__ void __launch_bounds__(kWarps * 32, 3)
+    spmm_short_d64_kernel(const int32_t* __restrict__ vptr, const int32_t* __restrict__ vrow,
+                          const int32_t* __restrict__ col, const float* __restrict__ val, const float* __restrict__ X,
+                          int64_t ldx, float* __restrict__ Y, int64_t ldy, float* __restrict__ partial, int64_t n_vrows,
+                          float alpha, float beta)
+{
+    using Ops = VecOps<float4>;
+    constexpr unsigned kFull = 0xffffffffu;
+    const int lane = threadIdx.x & 31, sub = lane & 15, half = lane >> 4;
+    const int64_t n_hw = (int64_t)gridDim.x * (kWarps * 2);  // half-warps in the grid (even: the two halves stay paired)
+    int64_t v = ((int64_t)blockIdx.x * (kWarps * 32) + threadIdx.x) >> 4;
+    const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+    const float4* __restrict__ Xl = reinterpret_cast<const float4*>(X) + sub;
+    const int64_t ldv = ldx >> 2;
+
+    auto load_ptr = [&](int64_t row, int& b, int& e, int& d) {
+        if (row < n_vrows) {
+            b = vptr[row];
+            e = vptr[row + 1];
+            d = IDENT ? (int)row : vrow[row];
+        } else {
+            b = e = d = 0;
+        }
+    };
+    auto load_cv = [&](int b, int e, int& c, float& w) {
+        c = 0;
+        w = 0.f;
+        if (b + sub < e) {
+            c = ld_stream_s32(col + b + sub, pol_stream);
+            w = ld_stream_f32(val + b + sub, pol_stream);
+        }
+    };
+    int b, e, dst, b1, e1, dst1, c;
+    float w;
+    load_ptr(v, b, e, dst);
+    load_cv(b, e, c, w);
+    load_ptr(v + n_hw, b1, e1, dst1);
+    while (v - half < n_vrows) {  // warp-uniform: half 1 of the last pair may idle on an empty row
+        int c1, b2, e2, dst2;
+        float w1;
+        load_cv(b1, e1, c1, w1);
+        load_ptr(v + 2 * n_hw, b2, e2, dst2);
+        const bool live = v < n_vrows;
+        const bool to_y = live && (IDENT || dst >= 0);
+        float4* yp = reinterpret_cast<float4*>(Y + (int64_t)(to_y ? dst : 0) * ldy) + sub;
+        float4 yold = Ops::zero();
+        if (to_y && beta != 0.f) yold = *yp;
+        const int n = e - b;
+        const int nmax = max(n, __shfl_xor_sync(kFull, n, 16));
+        float4 acc_e = Ops::zero(), acc_o = Ops::zero();
+        for (int base = 0; base < nmax; base += 16) {
+            if (base) load_cv(b + base, e, c, w);  // rows longer than 16 nonzeros: plain reload
+            const int m = n - base;
+            const int mm = min(16, nmax - base);
+            for (int j = 0; j < mm; j += 4) {
+                float4 xv[4];
+                float ww[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int cj = __shfl_sync(kFull, c, j + q, 16);
+                    ww[q] = __shfl_sync(kFull, w, j + q, 16);
+                    xv[q] = (j + q < m) ? Ops::gather(Xl + (int64_t)cj * ldv, pol_keep) : Ops::zero();
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (j + q < m) Ops::fma((q & 1) ? acc_o : acc_e, ww[q], xv[q]);
+            }
+        }
+        const float4 acc = Ops::add(acc_e, acc_o);
+        if (to_y)
+            *yp = (beta == 0.f) ? Ops::scale(alpha, acc) : Ops::axpby(alpha, acc, beta, yold);
+        else if (live)
+            reinterpret_cast<float4*>(partial + (int64_t)(-1 - dst) * 64)[sub] = acc;
+        v += n_hw;
+        b = b1; e = e1; dst = dst1; c = c1; w = w1;
+        b1 = b2; e1 = e2; dst1 = dst2;
+    }
+}
+
+// GMR_SPMM_SHORT: unset = pick by mean virtual-row length, 0 = never, 1 = whenever the shape allows.  Read on every call
+// (a getenv is noise next to a launch) so the tests can run both kernels in one process.
+static int spmm_short_mode()
+{
+    const char* s = getenv("GMR_SPMM_SHORT");
+    return (s && *s) ? atoi(s) : -1;
+}
+
 template <typename Vec, int LANES, int ITER, bool PUSH, bool OFF32, bool EXACT>
 static int launch_vrow2(const gmr_spmm_plan* plan, const int32_t* rowptr, const int32_t* col, const float* val,
                         const float* X, int64_t ldx, float* Y, int64_t ldy, float* partial, int32_t DV, float alpha,
@@ -367,7 +463,21 @@ static int dispatch(const gmr_spmm_plan* plan, const int32_t* rowptr, const int3
     constexpr int VEC = sizeof(Vec) / 4;
     const int32_t DV = D / VEC;
     int rc;
-    if (DV <= 16)
+    const int short_mode = spmm_short_mode();
+    if (VEC == 4 && DV == 16 && !PUSH && plan->n_vrows > 0 && short_mode != 0 &&
+        (short_mode > 0 || plan->nnz <= 12 * plan->n_vrows)) {
+        const int64_t want = (plan->n_vrows + 2 * kWarps - 1) / (2 * kWarps);
+        const int64_t cap = (int64_t)sm_count() * 3;
+        const unsigned grid = (unsigned)(want < cap ? want : cap);
+        if (plan->d_vptr == nullptr)
+            spmm_short_d64_kernel<true><<<grid, kWarps * 32, 0, st>>>(rowptr, nullptr, col, val, X, ldx, Y, ldy, partial,
+                                                                      plan->n_vrows, alpha, beta);
+        else
+            spmm_short_d64_kernel<false><<<grid, kWarps * 32, 0, st>>>(plan->d_vptr, plan->d_vrow, col, val, X, ldx, Y,
+                                                                       ldy, partial, plan->n_vrows, alpha, beta);
+        GMR_LAUNCH_CHECK();
+        rc = GMR_OK;
+    } else if (DV <= 16)
         rc = launch_vrow<Vec, 16, 1, PUSH>(plan, rowptr, col, val, X, ldx, Y, ldy, partial, DV, alpha, beta, push, st);
     else if (DV <= 32)
         rc = launch_vrow<Vec, 32, 1, PUSH>(plan, rowptr, col, val, X, ldx, Y, ldy, partial, DV, alpha, beta, push, st);

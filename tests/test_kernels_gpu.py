@@ -86,6 +86,44 @@ def test_spmm_chunk_sizes_agree(ops):
         assert rel(ops.spmm_raw(g, x).cpu().numpy(), ref) < 1e-5
 
 
+@pytest.mark.parametrize("shape", ["knn", "ragged_split", "tiny"])
+def test_spmm_short_row_kernel_is_bit_identical(ops, shape, monkeypatch):
+    """The half-warp-per-row variant (kNN / modal-mix graphs, D = 64) sums in the general kernel's order: forcing either
+    kernel through GMR_SPMM_SHORT must give identical bits, for whole rows, split rows, empty rows, rows past one
+    16-entry register stage, an odd row count (idle half-warp) and the alpha/beta/strided epilogue."""
+    rng = np.random.default_rng(17)
+    if shape == "knn":  # fixed 10 neighbours per row, identity plan
+        n_rows = n_cols = 4001
+        rowptr = (np.arange(n_rows + 1) * 10).astype(np.int32)
+        col = rng.integers(0, n_cols, size=n_rows * 10).astype(np.int32)
+        val = rng.standard_normal(col.size).astype(np.float32)
+    elif shape == "ragged_split":
+        n_rows, n_cols = 2777, 1900
+        rowptr, col, val = random_csr(rng, n_rows, n_cols, 5, long_rows=[(3, 900), (100, 17), (101, 33), (2776, 300)],
+                                      empty_rows=[0, 1, 50, 2775])
+    else:
+        n_rows, n_cols = 3, 5
+        rowptr, col, val = random_csr(rng, n_rows, n_cols, 2, empty_rows=[1])
+    g = to_graph(ops, rowptr, col, val, (n_rows, n_cols))
+    xw = torch.from_numpy(rng.standard_normal((n_cols, 128)).astype(np.float32)).cuda()
+    y0 = torch.from_numpy(rng.standard_normal((n_rows, 192)).astype(np.float32)).cuda()
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("GMR_SPMM_SHORT", mode)
+        plain = ops.spmm_raw(g, xw[:, :64].contiguous())
+        yw = y0.clone()
+        ops.spmm_raw(g, xw[:, 64:], out=yw[:, 64:128], alpha=0.25, beta=-1.5)
+        out[mode] = (plain, yw)
+    assert torch.equal(out["0"][0], out["1"][0])
+    assert torch.equal(out["0"][1], out["1"][1])
+    ref = c_api.spmm_csr_f64(rowptr, col, val, xw[:, :64].cpu().numpy())
+    assert rel(out["1"][0].cpu().numpy(), ref) < 1e-5
+    assert torch.equal(out["1"][1][:, :64], y0[:, :64]) and torch.equal(out["1"][1][:, 128:], y0[:, 128:])
+    monkeypatch.delenv("GMR_SPMM_SHORT")
+    auto = ops.spmm_raw(g, xw[:, :64].contiguous())  # the heuristic's pick, whichever it is
+    assert torch.equal(auto, out["0"][0])
+
+
 def test_spmm_backward_is_transpose(ops):
     rng = np.random.default_rng(5)
     rowptr, col, val = random_csr(rng, 300, 200, 6)
