@@ -499,8 +499,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="scaled", choices=sorted(WORKLOAD_NAMES))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("GMR_SCORE_PRECISION", "tc"), choices=["fp32", "tc"],
-                    help="scoring path: tc = tcgen05 split-bf16 + exact re-rank (same ids/scores as fp32)")
+    ap.add_argument("--precision", default=os.environ.get("GMR_SCORE_PRECISION", "tc"), choices=["fp32", "tc", "tc_split"],
+                    help="scoring path: tc = fp16 tcgen05 certified screen + exact fp32 re-score (default), tc_split = "
+                         "split-bf16 tcgen05 + exact re-rank, fp32 = CUDA cores; all three return the same ids/scores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay of the step")
     ap.add_argument("--no-extra-workloads", action="store_true")
