@@ -6,6 +6,13 @@ Same contract as ``TopKEvaluator`` of GenMMRec/src/utils/topk_evaluator.py:36-12
 prefix sums come from one kernel (csrc/metrics.cu) instead of a Python membership loop plus numpy
 (4.4 s of the reference's 5.1 s evaluation pass at the Baby shape).  The unrounded metric matrix of
 the last call is kept in ``last_raw`` for parity checks.
+
+With ``is_test=True`` the reference adds (topk_evaluator.py:123-270) Pop/Niche and Cold/Warm group metrics and the
+Coverage / Gini / Gini2 / Coverage2 / Tail% diversity numbers.  Here the group metrics are the same metrics kernel run on
+a filtered ground-truth CSR (popular or niche items only; warm or cold users only) built with device index ops instead of
+per-user Python list comprehensions, and the diversity numbers come from one device ``bincount`` per cut-off whose
+[n_items] result is reduced on the host with the reference's exact numpy expressions (integer counts, so the 4-decimal
+dict is identical).
 """
 import os
 
@@ -18,12 +25,34 @@ topk_metrics = {m.lower(): m for m in ["Recall", "Recall2", "Precision", "NDCG",
 _DEVICE_ROWS = {"recall": 0, "ndcg": 1, "precision": 2, "map": 3}
 
 
+def _cfg_get(config, key):
+    """``config[key] if key in config else None`` for both the Config class and plain dicts."""
+    try:
+        return config[key]
+    except KeyError:
+        return None
+
+
+def _gini_active(counts):
+    """``cal_gini`` of topk_evaluator.py:19-33 (Lorenz-curve Gini over the items that were recommended at least once,
+    with one zero appended), same operation order; ``np.trapz`` written out so it does not depend on the numpy version."""
+    cum = np.cumsum(np.sort(np.append(counts, 0)))
+    x = np.array(range(0, len(cum))) / (len(cum) - 1)
+    y = cum / cum[-1]
+    b = (np.diff(x) * (y[1:] + y[:-1]) / 2.0).sum(-1)
+    a = 0.5 - b
+    return a / (a + b)
+
+
 class TopKEvaluator(object):
     def __init__(self, config):
         self.config = config
         self.metrics = config["metrics"]
         self.topk = config["topk"]
         self.save_recom_result = config["save_recommended_topk"]
+        self.pop_items = _cfg_get(config, "pop_items")    # popular group, a set of item ids (quick_start.py:62-81)
+        self.warm_users = _cfg_get(config, "warm_users")  # users with > 5 train interactions (quick_start.py:85-92)
+        self._pop_mask = None
         self._check_args()
         self.last_raw = None
         self.last_hit = None
@@ -82,7 +111,95 @@ class TopKEvaluator(object):
         sums, hit = self.metric_sums(topk_index, eval_data, keep_hit=need_hit)
         out, raw = self.finalize(sums, topk_index.shape[0], hit, int(np.sum(eval_data.get_eval_len_list())))
         self.last_raw, self.last_hit, self.last_topk = raw, hit, topk_index
+        if is_test:
+            self._group_metrics(out, topk_index, eval_data)
+            self._diversity_metrics(out, topk_index, eval_data)
         return out
+
+    # ---- is_test extras (topk_evaluator.py:123-270) -------------------------------------------------
+    def _pop_mask_np(self, item_num):
+        """bool [item_num], True for popular items (ids outside the catalogue are ignored, topk_evaluator.py:217-222)."""
+        if self._pop_mask is None or self._pop_mask.shape[0] != item_num:
+            m = np.zeros(item_num, dtype=bool)
+            m[np.fromiter((i for i in self.pop_items if 0 <= i < item_num), dtype=np.int64)] = True
+            self._pop_mask = m
+        return self._pop_mask
+
+    def _subset_metrics(self, topk_i32, eval_data, prefix, out, item_keep=None, user_sel=None):
+        """Metrics over a sub-population: ground truth restricted to the entries flagged in ``item_keep`` (users left
+        without any are dropped, as in the reference's ``if len(gt_pop) > 0``) or to the users flagged in ``user_sel``."""
+        rowptr, items = eval_data.gt_rowptr, eval_data.gt_items
+        dev = rowptr.device
+        n_all = rowptr.numel() - 1
+        lens = rowptr[1:] - rowptr[:-1]
+        rows = torch.repeat_interleave(torch.arange(n_all, device=dev), lens)
+        keep = item_keep if item_keep is not None else torch.ones(items.numel(), dtype=torch.bool, device=dev)
+        if user_sel is not None:
+            keep = keep & user_sel[rows]
+        new_lens = torch.bincount(rows[keep], minlength=n_all)
+        users = user_sel if user_sel is not None else new_lens > 0
+        n = int(users.sum())
+        if n == 0:
+            return
+        sub_lens = new_lens[users]
+        sub_ptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        sub_ptr[1:] = torch.cumsum(sub_lens, dim=0)
+        need_hit = "recall2" in self.metrics
+        sums, hit = ops.hits_metrics(topk_i32[users].contiguous(), sub_ptr, items[keep].contiguous(), return_hit=need_hit)
+        res, _ = self.finalize(sums, n, hit, int(sub_lens.sum()))
+        for m in self.metrics:
+            for k in self.topk:
+                out["{}_{}@{}".format(prefix, topk_metrics.get(m, m), k)] = res["{}@{}".format(m, k)]
+
+    def _group_metrics(self, out, topk_index, eval_data):
+        if self.pop_items is None and self.warm_users is None:
+            return
+        dev = eval_data.gt_rowptr.device
+        topk_i32 = topk_index.to(device=dev, dtype=torch.int32)
+        if self.pop_items is not None:
+            pop_mask = torch.from_numpy(self._pop_mask_np(int(eval_data.dataset.item_num))).to(dev)
+            is_pop = pop_mask[eval_data.gt_items.long()]
+            self._subset_metrics(topk_i32, eval_data, "Pop", out, item_keep=is_pop)
+            self._subset_metrics(topk_i32, eval_data, "Niche", out, item_keep=~is_pop)
+        if self.warm_users is not None:
+            eval_users = eval_data.get_eval_users()
+            eval_users = eval_users.cpu().numpy() if torch.is_tensor(eval_users) else np.asarray(eval_users)
+            warm_ids = np.fromiter(self.warm_users, dtype=np.int64, count=len(self.warm_users))
+            is_warm = torch.from_numpy(np.isin(eval_users, warm_ids)).to(dev)
+            if bool((~is_warm).any()):
+                self._subset_metrics(topk_i32, eval_data, "Cold", out, user_sel=~is_warm)
+            if bool(is_warm.any()):
+                self._subset_metrics(topk_i32, eval_data, "Warm", out, user_sel=is_warm)
+
+    def _diversity_metrics(self, out, topk_index, eval_data):
+        item_num = int(eval_data.dataset.item_num)
+        pop_mask = self._pop_mask_np(item_num) if self.pop_items is not None else None
+        ids = topk_index.long()
+        for k in self.topk:
+            # the only pass over the [U, k] ids runs on the device; everything below is O(n_items) host arithmetic on
+            # exact integer counts, written as the reference writes it
+            rec_count = torch.bincount(ids[:, :k].reshape(-1), minlength=item_num).cpu().numpy()
+            n_rec = int(ids.shape[0]) * k
+            out["Coverage@{}".format(k)] = round(np.count_nonzero(rec_count) / item_num, 4)
+            sorted_counts = np.sort(rec_count)
+            n = item_num
+            sum_counts = np.cumsum(sorted_counts)[-1]
+            if sum_counts > 0:
+                index = np.arange(1, n + 1)
+                gini = (2 * np.sum(index * sorted_counts)) / (n * sum_counts) - (n + 1) / n
+                out["Gini@{}".format(k)] = round(gini, 4)
+            else:
+                out["Gini@{}".format(k)] = 0.0
+            active = rec_count[rec_count > 0]
+            if len(active) > 0:
+                out["Gini2@{}".format(k)] = round(_gini_active(active), 4)
+                out["Coverage2@{}".format(k)] = round(len(active) / item_num, 4)
+            else:
+                out["Gini2@{}".format(k)] = 0.0
+                out["Coverage2@{}".format(k)] = 0.0
+            if pop_mask is not None:
+                tail_count = rec_count[:item_num][~pop_mask].sum()
+                out["Tail%@{}".format(k)] = round(tail_count / n_rec, 4)
 
     def _dump(self, topk_index, eval_data, idx):
         """Tab-separated dump of the recommended ids (topk_evaluator.py:93-106)."""

@@ -3,6 +3,7 @@
 
     python tests/golden/make_golden.py            # toy fixtures for all six models + op fixtures
     python tests/golden/make_golden.py --baby     # additionally the Baby-shape samples
+    python tests/golden/make_golden.py --evaluator-only   # just the is_test evaluator dicts
 
 The reference holds no golden vectors of its own (five smoke scripts asserting a
 shape), so these files ARE the pin: the oracle (``oracle/``) is checked against them on CPU, and the
@@ -237,19 +238,94 @@ def op_fixtures(out_path):
     print("wrote", out_path, "%.1f KB" % (os.path.getsize(out_path) / 1024))
 
 
+def evaluator_fixtures(out_path):
+    """Known-answer dicts of the reference's own ``TopKEvaluator.evaluate(..., is_test=True)``
+    (utils/topk_evaluator.py:77-270): base metrics, Pop/Niche and Cold/Warm group metrics, Coverage / Gini / Gini2 /
+    Coverage2 / Tail%.  Two cases: with and without the popularity / warm-user groups quick_start.py:62-92 derives."""
+    rh.install_shims()
+    from utils.topk_evaluator import TopKEvaluator as RefEvaluator
+
+    class _Dataset:
+        def __init__(self, n):
+            self.item_num = n
+
+    class _EvalData:
+        def __init__(self, users, items_per_u, n_items):
+            self._u, self._items, self.dataset = users, items_per_u, _Dataset(n_items)
+
+        def get_eval_items(self):
+            return self._items
+
+        def get_eval_len_list(self):
+            return np.array([len(x) for x in self._items])
+
+        def get_eval_users(self):
+            return torch.from_numpy(self._u)
+
+    rng = np.random.default_rng(31)
+    n_users, n_items, k = 400, 150, 50
+    eval_users = rng.permutation(1000)[:n_users].astype(np.int64)
+    pop = np.sort(rng.choice(n_items, 30, replace=False)).astype(np.int64)
+    items_per_u = []
+    for u in range(n_users):
+        n = int(rng.integers(1, 9))
+        if u % 7 == 0:      # ground truth made of popular items only
+            g = rng.choice(pop, min(n, 5), replace=False)
+        elif u % 7 == 1:    # niche items only
+            g = rng.choice(np.setdiff1d(np.arange(n_items), pop), n, replace=False)
+        else:
+            g = rng.choice(n_items, n, replace=False)
+        items_per_u.append(np.sort(g).astype(np.int64))
+    # recommendations: popularity-skewed permutations so that hits, coverage gaps and never-recommended items all occur
+    w = 1.0 / (1.0 + np.arange(n_items)) ** 0.9
+    w = w[rng.permutation(n_items)]
+    topk = np.stack([rng.choice(n_items - 10, k, replace=False, p=w[:n_items - 10] / w[:n_items - 10].sum())
+                     for _ in range(n_users)]).astype(np.int64)
+    warm = np.sort(eval_users[rng.random(n_users) < 0.6])
+    warm = np.concatenate([warm, np.array([5000, 5001])])  # ids outside the eval set are legal in the set
+    out = {"topk": topk.astype(np.int32), "eval_users": eval_users, "n_items": np.int64(n_items),
+           "gt_rowptr": np.concatenate([[0], np.cumsum([len(x) for x in items_per_u])]).astype(np.int64),
+           "gt_items": np.concatenate(items_per_u).astype(np.int32), "pop_items": pop, "warm_users": warm}
+    cases = {
+        "groups": dict(metrics=["Recall", "NDCG", "Precision", "MAP", "Recall2"], topk=[5, 10, 20, 50],
+                       pop_items=set(pop.tolist()), warm_users=set(warm.tolist())),
+        "plain": dict(metrics=["Recall", "NDCG", "Precision", "MAP"], topk=[10, 50]),
+    }
+    for name, cfg in cases.items():
+        cfg = dict(cfg, save_recommended_topk=False)
+        ev = RefEvaluator(cfg)
+        data = _EvalData(eval_users, items_per_u, n_items)
+        res_test = ev.evaluate([torch.from_numpy(topk)], data, is_test=True)
+        res_valid = RefEvaluator(cfg).evaluate([torch.from_numpy(topk)], data, is_test=False)
+        out[name + "/metrics"] = np.array(cfg["metrics"])
+        out[name + "/topk_list"] = np.array(cfg["topk"], dtype=np.int64)
+        out[name + "/test_keys"] = np.array(list(res_test.keys()))
+        out[name + "/test_values"] = np.array([float(v) for v in res_test.values()], dtype=np.float64)
+        out[name + "/valid_keys"] = np.array(list(res_valid.keys()))
+        out[name + "/valid_values"] = np.array([float(v) for v in res_valid.values()], dtype=np.float64)
+        print(name, len(res_test), "keys, e.g.", {q: res_test[q] for q in list(res_test)[-6:]})
+    np.savez_compressed(out_path, **out)
+    print("wrote", out_path, "%.1f KB" % (os.path.getsize(out_path) / 1024))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--baby", action="store_true")
     ap.add_argument("--models", default="DiffMM,GUME,GenRecV1,LD4MRec,VBPR,LightGCN")
     ap.add_argument("--skip-toy", action="store_true")
+    ap.add_argument("--evaluator-only", action="store_true", help="only (re)write evaluator_extras.npz")
     args = ap.parse_args()
     assert rh.reference_available(), "reference tree not found at %s" % rh.REF_ROOT
     torch.set_num_threads(os.cpu_count())
+    if args.evaluator_only:
+        evaluator_fixtures(os.path.join(HERE, "evaluator_extras.npz"))
+        return
     models = args.models.split(",")
     tmp = tempfile.mkdtemp(prefix="gmr_golden_")
     try:
         if not args.skip_toy:
             op_fixtures(os.path.join(HERE, "ops.npz"))
+            evaluator_fixtures(os.path.join(HERE, "evaluator_extras.npz"))
             synth.write_dataset(tmp, "toy", TOY["n_users"], TOY["n_items"], TOY["n_inter"],
                                 image_dim=TOY["image_dim"], text_dim=TOY["text_dim"])
             for name in models:
