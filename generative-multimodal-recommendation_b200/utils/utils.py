@@ -48,3 +48,20 @@ def build_knn_normalized_graph(adj, topk, is_sparse=True, norm_type="sym"):
     val, ind = torch.topk(adj, topk, dim=-1)
     idx, w, shape = _graph.knn_from_topk(val, ind)
     return torch.sparse_coo_tensor(idx, w, shape)
+
+
+def set_popularity_groups(config, train_dataset, pop_fraction=0.2, cold_start_threshold=5):
+    """Fill ``config['pop_items']`` / ``config['warm_users']`` the way the reference's entry point does before it builds
+    the trainer (GenMMRec/src/utils/quick_start.py:46-92): popular items = the first ``int(0.2 * n_unique)`` item ids of
+    the train split ordered by interaction count (``value_counts``), warm users = users with more than five train
+    interactions.  The evaluator reads both for the ``is_test`` group metrics.  Uses the same pandas call as the
+    reference so that ties at the 20 % boundary fall the same way."""
+    import pandas as pd
+
+    items = train_dataset.items.cpu().numpy()
+    users = train_dataset.users.cpu().numpy()
+    unique_items = pd.Series(items).value_counts().index.tolist()
+    config["pop_items"] = set(unique_items[:int(len(unique_items) * pop_fraction)])
+    user_counts = pd.Series(users).value_counts()
+    config["warm_users"] = set(user_counts[user_counts > cold_start_threshold].index.tolist())
+    return config

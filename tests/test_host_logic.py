@@ -140,3 +140,25 @@ def test_registry():
     for name in ("DiffMM", "GUME", "GenRecV1", "LD4MRec", "VBPR", "LightGCN"):
         assert get_model(name).__name__ == name
     assert get_trainer("DiffMM").__name__ == "Trainer"
+
+
+def test_popularity_groups_follow_quick_start():
+    """quick_start.py:46-92: top 20 % of the train items by count are 'popular', users with > 5 train rows are 'warm'."""
+    from genmmrec_b200.utils.utils import set_popularity_groups
+
+    class _Train:
+        pass
+
+    rng = np.random.default_rng(8)
+    tr = _Train()
+    tr.items = torch.from_numpy(rng.zipf(1.6, size=4000).clip(max=300).astype(np.int64) - 1)
+    tr.users = torch.from_numpy(rng.integers(0, 500, size=4000))
+    cfg = set_popularity_groups({}, tr)
+    counts = np.bincount(tr.items.numpy())
+    seen = np.flatnonzero(counts)
+    pop = np.array(sorted(cfg["pop_items"]))
+    assert len(pop) == int(len(seen) * 0.2) and set(pop) <= set(seen)
+    rest = np.setdiff1d(seen, pop)
+    assert counts[pop].min() >= counts[rest].max()
+    ucounts = np.bincount(tr.users.numpy(), minlength=500)
+    assert cfg["warm_users"] == set(np.flatnonzero(ucounts > 5).tolist())
