@@ -1,0 +1,107 @@
+"""Property tests of the oracle itself (CPU): the C restatement (oracle/gmr_oracle.c), the numpy port
+(oracle/ref_port.py) and the literal torch / Python expressions of the reference must agree on random inputs, including
+the cases the golden files hold only a few of: tied scores, masks that leave fewer than K items, duplicate and empty
+CSR rows, ground truth longer than K.  Reference expressions: common/trainer.py:379-387 (mask + topk),
+utils/topk_evaluator.py:107-111 (hit matrix), utils/metrics.py:12-105."""
+import numpy as np
+import torch
+from hypothesis import given, settings, strategies as st
+
+from oracle import c_api, ref_port as rp
+
+SETTINGS = dict(max_examples=25, deadline=None)
+
+
+@settings(**SETTINGS)
+@given(seed=st.integers(0, 2**31 - 1), b=st.integers(1, 9), n_items=st.integers(1, 70), d=st.sampled_from([1, 3, 8, 64]),
+       k=st.integers(1, 20), with_bias=st.booleans(), mask_avg=st.sampled_from([0.0, 0.3, 0.95]))
+def test_score_mask_topk_oracle_vs_reference_expression(seed, b, n_items, d, k, with_bias, mask_avg):
+    k = min(k, n_items)
+    rng = np.random.default_rng(seed)
+    n_users = b + 3
+    eu = rng.standard_normal((n_users, d)).astype(np.float32)
+    ei = rng.standard_normal((n_items, d)).astype(np.float32)
+    users = rng.integers(0, n_users, size=b).astype(np.int64)
+    bias = rng.standard_normal(n_items).astype(np.float32) if with_bias else None
+    m = rng.random((b, n_items)) < mask_avg
+    rows, cols = np.nonzero(m)
+    rowptr = np.concatenate([[0], np.cumsum(m.sum(1))]).astype(np.int64)
+    ids, sc = c_api.score_mask_topk(eu, users, ei, bias, rowptr, cols.astype(np.int32), k)
+    # the reference: full_sort_predict -> index_put_(-1e10) -> torch.topk
+    s = torch.from_numpy(eu)[torch.from_numpy(users)] @ torch.from_numpy(ei).T
+    if with_bias:
+        s = s + torch.from_numpy(bias)
+    s[torch.from_numpy(rows), torch.from_numpy(cols)] = -1e10
+    val, idx = torch.topk(s, k, dim=-1)
+    scale = max(float(s[s > -1e9].abs().max()) if bool((s > -1e9).any()) else 1.0, 1.0)
+    assert np.abs(sc - val.numpy()).max() <= 1e-5 * scale  # same multiset of scores, position by position
+    for r in range(b):
+        # order contract: score descending, id ascending among equals; no item twice
+        assert len(set(ids[r].tolist())) == k
+        for j in range(1, k):
+            assert sc[r, j - 1] > sc[r, j] or (sc[r, j - 1] == sc[r, j] and ids[r, j - 1] < ids[r, j])
+        # ids equal to torch.topk wherever the neighbouring reference scores are not within rounding of each other
+        v = val[r].numpy()
+        for j in range(k):
+            lo = v[j] - v[j + 1] if j + 1 < k else np.inf
+            hi = v[j - 1] - v[j] if j > 0 else np.inf
+            if min(lo, hi) > 1e-4 * scale and v[j] > -1e9:
+                assert ids[r, j] == int(idx[r, j])
+        unmasked = int((~m[r]).sum())
+        assert np.all(~m[r][ids[r, :min(k, unmasked)]])  # masked items only after every unmasked one
+
+
+def test_tied_scores_are_ordered_by_item_id():
+    rng = np.random.default_rng(5)
+    base = rng.standard_normal((6, 16)).astype(np.float32)
+    ei = np.concatenate([base, base, base])[rng.permutation(18)]  # every score appears three times
+    eu = rng.standard_normal((4, 16)).astype(np.float32)
+    ids, sc = c_api.score_mask_topk(eu, None, ei, None, None, None, 18)
+    for r in range(4):
+        order = np.lexsort((np.arange(18), -(sc[r].astype(np.float64))))
+        assert np.array_equal(order, np.arange(18))
+        for j in range(0, 18, 3):
+            assert sc[r, j] == sc[r, j + 1] == sc[r, j + 2] and ids[r, j] < ids[r, j + 1] < ids[r, j + 2]
+
+
+@settings(**SETTINGS)
+@given(seed=st.integers(0, 2**31 - 1), u=st.integers(1, 30), k=st.integers(1, 50), n_items=st.integers(50, 200),
+       max_len=st.integers(1, 80))
+def test_hits_and_metrics_oracles_vs_reference_expressions(seed, u, k, n_items, max_len):
+    rng = np.random.default_rng(seed)
+    topk = np.stack([rng.choice(n_items, size=k, replace=False) for _ in range(u)]).astype(np.int32)
+    gts = [np.sort(rng.choice(n_items, size=int(rng.integers(1, min(max_len, n_items) + 1)), replace=False))
+           for _ in range(u)]
+    rowptr = np.concatenate([[0], np.cumsum([len(g) for g in gts])]).astype(np.int64)
+    hit = c_api.hits(topk, rowptr, np.concatenate(gts).astype(np.int32))
+    want = np.asarray([[True if i in m else False for i in n] for m, n in zip(gts, topk)])  # topk_evaluator.py:108-110
+    assert np.array_equal(hit.astype(bool), want)
+    pos_len = np.array([len(g) for g in gts], dtype=np.int64)
+    c = c_api.metrics(hit, pos_len)
+    for name in ("recall", "ndcg", "precision", "map"):
+        assert np.abs(c[name] - rp.METRICS[name](want, pos_len)).max() < 1e-12, name
+    assert np.all(np.diff(c["recall"]) >= -1e-15) and c["recall"][-1] <= 1 + 1e-15
+    assert np.all((c["ndcg"] >= 0) & (c["ndcg"] <= 1 + 1e-12))
+
+
+@settings(**SETTINGS)
+@given(seed=st.integers(0, 2**31 - 1), n_rows=st.integers(1, 40), n_cols=st.integers(1, 40), d=st.sampled_from([1, 5, 64]),
+       nnz=st.integers(0, 300))
+def test_spmm_oracles_vs_dense(seed, n_rows, n_cols, d, nnz):
+    rng = np.random.default_rng(seed)
+    r = np.sort(rng.integers(0, n_rows, size=nnz))
+    c = rng.integers(0, n_cols, size=nnz)  # duplicates (r, c) allowed: they add, as in an uncoalesced COO
+    v = rng.standard_normal(nnz).astype(np.float32)
+    x = rng.standard_normal((n_cols, d)).astype(np.float32)
+    dense = np.zeros((n_rows, n_cols), dtype=np.float64)
+    np.add.at(dense, (r, c), v.astype(np.float64))
+    want = dense @ x.astype(np.float64)
+    rowptr = np.concatenate([[0], np.cumsum(np.bincount(r, minlength=n_rows))]).astype(np.int32)
+    scale = max(np.abs(want).max(), 1e-30)
+    y_csr = c_api.spmm_csr(rowptr, c.astype(np.int32), v, x)
+    y_coo = c_api.spmm_coo(r, c, v, x, n_rows)
+    assert np.abs(y_csr - want).max() <= 1e-5 * scale + 1e-30
+    assert np.abs(y_coo - want).max() <= 1e-5 * scale + 1e-30
+    y0 = rng.standard_normal((n_rows, d)).astype(np.float32)
+    y_ab = c_api.spmm_csr(rowptr, c.astype(np.int32), v, x, alpha=0.5, beta=-2.0, y=y0.copy())
+    assert np.abs(y_ab - (0.5 * want - 2.0 * y0)).max() <= 1e-5 * max(scale, np.abs(y0).max() * 2) + 1e-30
