@@ -10,7 +10,6 @@ import torch.nn as nn
 
 from ..common.abstract_recommender import GeneralRecommender
 from .. import graph as gb
-from ..ops import spmm
 from ._common import BipartiteAdj, bpr_loss, emb_loss
 
 

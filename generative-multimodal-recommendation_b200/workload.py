@@ -6,7 +6,6 @@ generated directly on the GPU with the same recipe (heavy-tailed user degrees, r
 popularity, unique pairs, per-user leave-two-out split) because a host-side build would dominate
 the run.
 """
-import numpy as np
 import torch
 
 from . import synth

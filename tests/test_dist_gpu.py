@@ -103,7 +103,6 @@ def test_modal_mix_graph_equals_two_products(mods):
 def test_sharded_diffmm_world1_equals_model(mods):
     gd, ops = mods
     from test_models_gpu import build, load_params, set_graphs
-    import test_models_gpu as tm
 
     class Env:
         pass
