@@ -83,6 +83,36 @@ def test_is_test_extras_match_reference_dicts_host_logic(case, monkeypatch):
                 "Gini2@5", "Coverage2@20"} <= keys
 
 
+def test_recommendation_dump_has_the_reference_file_format(tmp_path, monkeypatch):
+    """topk_evaluator.py:93-106: tab-separated, header ``id top_0 .. top_{K-1}``, one integer row per eval user, written
+    only when ``save_recommended_topk`` is set and ``is_test`` is true."""
+    import glob
+    import os
+
+    import pandas as pd
+
+    from genmmrec_b200 import ops
+    from genmmrec_b200.utils.topk_evaluator import TopKEvaluator
+
+    z, _ = load_golden("evaluator_extras")
+    monkeypatch.setattr(ops, "hits_metrics", _oracle_hits_metrics)
+    cfg = dict(_config(z, "plain"), save_recommended_topk=True, recommend_topk=str(tmp_path / "rec"), model="DiffMM",
+               dataset="toy")
+    data = _EvalData(z, "cpu")
+    ev = TopKEvaluator(cfg)
+    ev.evaluate(torch.from_numpy(z["topk"]), data, is_test=False)
+    assert not os.path.exists(cfg["recommend_topk"])
+    ev.evaluate(torch.from_numpy(z["topk"]), data, is_test=True, idx=3)
+    files = glob.glob(os.path.join(cfg["recommend_topk"], "DiffMM-toy-idx3-top50-*.csv"))
+    assert len(files) == 1
+    want = pd.DataFrame(z["topk"])  # the reference's own construction
+    want.insert(0, "id", z["eval_users"])
+    want.columns = ["id"] + ["top_" + str(i) for i in range(50)]
+    want_path = tmp_path / "want.csv"
+    want.astype(int).to_csv(want_path, sep="\t", index=False)
+    assert open(files[0]).read() == open(want_path).read()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", ["groups", "plain"])
 def test_is_test_extras_match_reference_dicts_on_device(case):
