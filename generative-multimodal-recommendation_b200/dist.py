@@ -472,3 +472,25 @@ def shard_eval_by_user_block(loader, u0, u1):
     s.eval_len_list = np.asarray(loader.eval_len_list)[sel.cpu().numpy()]
     s.get_eval_len_list = lambda: s.eval_len_list
     return s
+
+
+def evaluate_sharded(sharded, evaluator, shard, k=None, precision="tc", group=None):
+    """One sharded evaluation pass, the multi-GPU form of ``Trainer.evaluate`` (common/trainer.py:369-388 of the
+    reference): this rank's propagated factors (``sharded.eval_factors()`` of a ``ShardedDiffMM`` / ``ShardedGCNChain``)
+    -> fused score + mask + top-K over its user block (``shard`` from ``shard_eval_by_user_block``) -> hit / metric SUMS
+    -> all-reduce of the ``[4, K]`` float64 sums and the user count -> the reference's rounded dict, identical on every
+    rank.  Returns ``(dict, unrounded [n_metrics, K], local top-K ids)``.  ``recall2`` needs the global hit matrix and
+    is not available here."""
+    import torch.distributed as dist
+
+    k = int(k or max(evaluator.topk))
+    ue, ie = sharded.eval_factors()
+    ids, _ = ops.score_mask_topk(ue.contiguous(), ie.contiguous(), k, users=shard.eval_u, mask_rowptr=shard.mask_rowptr,
+                                 mask_items=shard.mask_items, precision=precision, return_scores=False)
+    sums, _ = evaluator.metric_sums(ids, shard)
+    n = torch.tensor([float(ids.shape[0])], dtype=torch.float64, device=sums.device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(sums, group=group)
+        dist.all_reduce(n, group=group)
+    out, raw = evaluator.finalize(sums, int(round(float(n.item()))))
+    return out, raw, ids

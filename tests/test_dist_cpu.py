@@ -65,6 +65,40 @@ def _worker(rank, world, port, out):
         dist.all_reduce(sums)
         want = np.stack([m_all[k] for k in ("recall", "ndcg", "precision", "map")])
         assert np.abs(sums.numpy() / loader.eval_u.numel() - want).max() < 1e-12
+        # dist.evaluate_sharded: the same composition with the oracle standing in for the two kernels; the dict must
+        # equal the unsharded one on every rank
+        from genmmrec_b200 import ops
+        from genmmrec_b200.utils.topk_evaluator import TopKEvaluator
+
+        def fake_score(ue, ie, kk, users=None, mask_rowptr=None, mask_items=None, precision="tc", return_scores=False):
+            ids_, sc_ = c_api.score_mask_topk(ue.numpy(), users.numpy(), ie.numpy(), None, mask_rowptr.numpy(),
+                                              mask_items.numpy(), kk)
+            return torch.from_numpy(ids_), None
+
+        def fake_hits(topk_, gt_rowptr, gt_items, return_hit=False):
+            h = c_api.hits(topk_.numpy(), gt_rowptr.numpy(), gt_items.numpy())
+            m = c_api.metrics(h, np.diff(gt_rowptr.numpy()))
+            return torch.from_numpy(np.stack([m[q] for q in ("recall", "ndcg", "precision", "map")]) * topk_.shape[0]), None
+
+        ops.score_mask_topk, ops.hits_metrics = fake_score, fake_hits
+        g = torch.Generator().manual_seed(3)
+        ue_all, ie_all = torch.randn(300, 16, generator=g), torch.randn(120, 16, generator=g)
+
+        class _Factors:
+            def __init__(self, ue, ie):
+                self.ue, self.ie = ue, ie
+
+            def eval_factors(self):
+                return self.ue, self.ie
+
+        ev = TopKEvaluator({"metrics": ["Recall", "NDCG", "Precision", "MAP"], "topk": [5, 10, 20],
+                            "save_recommended_topk": False})
+        got, raw, ids_loc = gd.evaluate_sharded(_Factors(ue_all[ub[rank]:ub[rank + 1]], ie_all), ev, sh, precision="fp32")
+        ids_all, _ = fake_score(ue_all, ie_all, 20, users=loader.eval_u, mask_rowptr=loader.mask_rowptr,
+                                mask_items=loader.mask_items)
+        assert torch.equal(ids_loc, ids_all[sh.positions])
+        want_dict = ev.evaluate(ids_all, loader)
+        assert got == want_dict and np.abs(raw - ev.last_raw).max() < 1e-12
         out.put((rank, "ok"))
     except Exception as e:  # surface the failure in the parent
         import traceback
