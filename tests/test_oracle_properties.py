@@ -9,7 +9,7 @@ from hypothesis import given, settings, strategies as st
 
 from oracle import c_api, ref_port as rp
 
-SETTINGS = dict(max_examples=25, deadline=None)
+SETTINGS = dict(max_examples=40, deadline=None, derandomize=True)  # fixed example sequence: no run-to-run flakiness
 
 
 @settings(**SETTINGS)
