@@ -30,6 +30,12 @@ SIGNATURES = {
     "gmr_spmm_csr_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i32, _f32, _f32, _vp, _i64, _vp]),
     "gmr_spmm_csr_f32_push": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i64, _i64, _i32, _f32, _vp, _i64,
                                         _vp]),
+    "gmr_spmm_blocked_plan_create": (C.c_int, [C.POINTER(_vp), _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
+    "gmr_spmm_blocked_plan_set_values": (C.c_int, [_vp, _vp, _vp]),
+    "gmr_spmm_blocked_plan_destroy": (C.c_int, [_vp]),
+    "gmr_spmm_blocked_plan_stats": (C.c_int, [_vp, C.POINTER(_i64)]),
+    "gmr_spmm_blocked_workspace_bytes": (_i64, [_vp, _i32]),
+    "gmr_spmm_blocked_f32": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i32, _f32, _f32, _vp, _i64, _vp]),
     "gmr_rows_push_f32": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _i32, _i64, _i64, _vp]),
     "gmr_score_topk_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32, _i32]),
     "gmr_score_mask_topk_f32": (C.c_int, [_vp, _i64, _vp, _i32, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _i32, _i32, _vp,

@@ -7,6 +7,8 @@
 // result is run-to-run deterministic and within a few ulp of numpy's pairwise sum.
 #include <cmath>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "topk_select.cuh"
 
@@ -134,7 +136,10 @@ __global__ void __launch_bounds__(256) metrics_final_kernel(const double* __rest
     if (threadIdx.x == 0) sums[blockIdx.x] = red[0];
 }
 
-static bool g_discount_ready = false;
+// one flag per device: the __constant__ table exists once per device (a second GPU driven from the same process
+// would otherwise run with an all-zero table); the mutex makes the lazy upload thread-safe
+static bool g_discount_ready[64] = {false};
+static std::mutex g_discount_mu;
 
 }  // namespace gmr
 
@@ -164,12 +169,20 @@ extern "C" int gmr_hits_metrics(const int32_t* topk, const int64_t* gt_rowptr, c
                        (long long)workspace_bytes);
         return GMR_ERR_WORKSPACE;
     }
-    if (!gmr::g_discount_ready) {
-        // same expression as GenMMRec/src/utils/metrics.py:53,59: 1.0 / np.log2(rank + 1), rank = k + 1
-        double h[GMR_MAX_TOPK];
-        for (int k = 0; k < GMR_MAX_TOPK; ++k) h[k] = 1.0 / std::log2((double)k + 2.0);
-        GMR_CHECK_CUDA(cudaMemcpyToSymbol(gmr::c_discount, h, sizeof(h)));
-        gmr::g_discount_ready = true;
+    {
+        int dev = 0;
+        GMR_CHECK_CUDA(cudaGetDevice(&dev));
+        GMR_REQUIRE(dev >= 0 && dev < 64, "gmr_hits_metrics: device ordinal %d outside [0, 64)", dev);
+        std::lock_guard<std::mutex> lock(gmr::g_discount_mu);
+        if (!gmr::g_discount_ready[dev]) {
+            // same expression as GenMMRec/src/utils/metrics.py:53,59: 1.0 / np.log2(rank + 1), rank = k + 1.
+            // Synchronous copy: the first call on a device must not happen inside a CUDA-graph capture
+            // (Trainer.graphed runs the step eagerly first).
+            double h[GMR_MAX_TOPK];
+            for (int k = 0; k < GMR_MAX_TOPK; ++k) h[k] = 1.0 / std::log2((double)k + 2.0);
+            GMR_CHECK_CUDA(cudaMemcpyToSymbol(gmr::c_discount, h, sizeof(h)));
+            gmr::g_discount_ready[dev] = true;
+        }
     }
     const int nb = (int)(((int64_t)U + gmr::kMU - 1) / gmr::kMU);
     gmr::hits_metrics_kernel<<<nb, gmr::kMU, 0, st>>>(topk, gt_rowptr, gt_items, U, K, hit, (double*)workspace);

@@ -5,6 +5,7 @@ computation below is a call into the hand-written sm_100a kernels through the C 
 (``include/gmr.h``).  Nothing in this module has a CPU or eager-PyTorch fallback.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -82,6 +83,7 @@ class GraphCSR:
         self.device = rowptr.device
         self.chunk_nnz = chunk_nnz
         self._plan = None
+        self._bplans = {}   # block_cols -> [handle, version of `val` the plan snapshotted]
         self._t = None
         self._coo = None
 
@@ -153,6 +155,34 @@ class GraphCSR:
             self._plan = h
         return self._plan
 
+    def blocked_plan(self, block_cols):
+        """Column-blocked plan (K1b, csrc/spmm_flat.cu) with blocks of `block_cols` columns.  The plan snapshots the
+        matrix; if `val` was modified in place since (its torch version counter moved) the values are re-read."""
+        lib = _lib.load()
+        block_cols = int(min(max(1, block_cols), max(1, self.shape[1])))
+        ent = self._bplans.get(block_cols)
+        if ent is None:
+            h = C.c_void_p()
+            with torch.cuda.device(self.device):
+                _lib.check(lib.gmr_spmm_blocked_plan_create(C.byref(h), _ptr(self.rowptr), _ptr(self.col), _ptr(self.val),
+                                                            self.shape[0], self.shape[1], block_cols, _stream()),
+                           "gmr_spmm_blocked_plan_create")
+            ent = [h, self.val._version]
+            self._bplans[block_cols] = ent
+        elif ent[1] != self.val._version:
+            with torch.cuda.device(self.device):
+                _lib.check(lib.gmr_spmm_blocked_plan_set_values(ent[0], _ptr(self.val), _stream()),
+                           "gmr_spmm_blocked_plan_set_values")
+            ent[1] = self.val._version
+        return ent[0]
+
+    def blocked_plan_stats(self, block_cols):
+        lib = _lib.load()
+        out = (C.c_int64 * 8)()
+        _lib.check(lib.gmr_spmm_blocked_plan_stats(self.blocked_plan(block_cols), out), "gmr_spmm_blocked_plan_stats")
+        keys = ("blocks", "block_cols", "tiles", "segments", "long_segments", "slots", "reduce_small", "reduce_big")
+        return dict(zip(keys, [int(v) for v in out]))
+
     def plan_stats(self):
         lib = _lib.load()
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
@@ -167,8 +197,30 @@ class GraphCSR:
         try:
             if self._plan is not None and _lib._lib is not None:
                 _lib._lib.gmr_spmm_plan_destroy(self._plan)
+            if _lib._lib is not None:
+                for h, _ in self._bplans.values():
+                    _lib._lib.gmr_spmm_blocked_plan_destroy(h)
         except Exception:
             pass
+
+
+# Column blocking (K1b, csrc/spmm_flat.cu) is OPT-IN: on the 1M x 500k workload it ties the row-centric kernels (2.47 vs
+# 2.41 ms for the full graph, profiles/r02_spmm_flat_probe_v6.json) while cutting DRAM traffic 4.5x, so the default stays
+# K1.  GMR_SPMM_BLOCKED: 0 (default) = row-centric kernels; auto = block when the gathered table n_cols * D * 4 exceeds
+# GMR_SPMM_BLOCK_MIN_MB (96); 1 = always the nonzero-centric kernel.  GMR_SPMM_BLOCK_MB (48) is the slice of X one pass
+# gathers from.
+def _block_cols_for(a, d, x, out):
+    mode = os.environ.get("GMR_SPMM_BLOCKED", "0")
+    if mode == "0" or d % 4 != 0:
+        return None
+    if x.data_ptr() % 16 or out.data_ptr() % 16 or (x.shape[0] > 1 and x.stride(0) % 4) or (out.shape[0] > 1 and out.stride(0) % 4):
+        return None
+    row_bytes = d * 4
+    table = a.shape[1] * row_bytes
+    if mode != "1" and table <= (int(os.environ.get("GMR_SPMM_BLOCK_MIN_MB", "96")) << 20):
+        return None
+    target = int(os.environ.get("GMR_SPMM_BLOCK_MB", "48")) << 20
+    return max(1, min(a.shape[1], target // row_bytes))
 
 
 def spmm_raw(a, x, out=None, alpha=1.0, beta=0.0):
@@ -187,6 +239,9 @@ def spmm_raw(a, x, out=None, alpha=1.0, beta=0.0):
     yp, ldy = _rows(out, "Y")
     if out.shape != (a.shape[0], d):
         raise ValueError("spmm: out has shape %s, expected %s" % (tuple(out.shape), (a.shape[0], d)))
+    bc = _block_cols_for(a, d, x, out) if a.shape[0] > 0 else None
+    if bc is not None:
+        return spmm_blocked(a, x, bc, out=out, alpha=alpha, beta=beta)
     plan = a.plan
     need = lib.gmr_spmm_workspace_bytes(plan, d)
     ws = _ws(x.device, need, "spmm") if need > 0 else None
@@ -194,8 +249,38 @@ def spmm_raw(a, x, out=None, alpha=1.0, beta=0.0):
         ev = _prof_begin()
         _lib.check(lib.gmr_spmm_csr_f32(plan, _ptr(a.rowptr), _ptr(a.col), _ptr(a.val), xp, ldx, yp, ldy, d,
                                         float(alpha), float(beta), _ptr(ws), need, _stream()), "gmr_spmm_csr_f32")
-        _prof_end("spmm", ev, alg_bytes=a.algorithmic_bytes(d), nnz=a.nnz, d=d, rows=a.shape[0], cols=a.shape[1])
+        _prof_end("spmm", ev, alg_bytes=a.algorithmic_bytes(d), nnz=a.nnz, d=d, rows=a.shape[0], cols=a.shape[1],
+                  kernel="row")
     LAUNCHES += 1 + (1 if need > 0 else 0)
+    return out
+
+
+def spmm_blocked(a, x, block_cols, out=None, alpha=1.0, beta=0.0):
+    """Y = alpha * A @ X + beta * Y through K1b (column-blocked, nonzero-centric; csrc/spmm_flat.cu) with blocks of
+    `block_cols` columns.  D % 4 == 0 and 16-byte aligned rows required."""
+    global LAUNCHES
+    lib = _lib.load()
+    if x.shape[0] != a.shape[1]:
+        raise ValueError("spmm: A is %s but X has %d rows" % (a.shape, x.shape[0]))
+    d = int(x.shape[1])
+    if out is None:
+        if beta != 0.0:
+            raise ValueError("spmm: beta != 0 needs an `out` to accumulate into")
+        out = torch.empty((a.shape[0], d), dtype=torch.float32, device=x.device)
+    xp, ldx = _rows(x, "X")
+    yp, ldy = _rows(out, "Y")
+    if out.shape != (a.shape[0], d):
+        raise ValueError("spmm: out has shape %s, expected %s" % (tuple(out.shape), (a.shape[0], d)))
+    bplan = a.blocked_plan(block_cols)
+    need = lib.gmr_spmm_blocked_workspace_bytes(bplan, d)
+    ws = _ws(x.device, need, "spmm") if need > 0 else None
+    with torch.cuda.device(x.device):
+        ev = _prof_begin()
+        _lib.check(lib.gmr_spmm_blocked_f32(bplan, xp, ldx, yp, ldy, d, float(alpha), float(beta), _ptr(ws), need,
+                                            _stream()), "gmr_spmm_blocked_f32")
+        _prof_end("spmm", ev, alg_bytes=a.algorithmic_bytes(d), nnz=a.nnz, d=d, rows=a.shape[0], cols=a.shape[1],
+                  kernel="flat/blocked", block_cols=int(block_cols))
+    LAUNCHES += -(-a.shape[1] // max(1, int(block_cols))) + 2
     return out
 
 

@@ -74,6 +74,29 @@ int gmr_spmm_csr_f32(const gmr_spmm_plan_t* plan, const int32_t* rowptr, const i
                      const float* X, int64_t ldx, float* Y, int64_t ldy, int32_t D, float alpha, float beta,
                      void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * K1b  column-blocked, nonzero-centric SpMM (same operator and call sites as K1) for graphs whose
+ * gathered operand does not fit the L2.  The blocked plan SNAPSHOTS the matrix: it stably sorts the
+ * nonzeros by column block (blocks of `block_cols` columns; 0 = one block) and keeps its own
+ * (row, col, val) arrays, so the product takes no CSR arguments.  One pass per block runs back to
+ * back on the stream (each gathers from an L2-resident slice of X), Y is accumulated across
+ * passes.  Per-row summation order is canonical (pieces of 64 nonzeros counted from the start of a
+ * row's block segment, blocks ascending): results are run-to-run deterministic and do not depend
+ * on which other rows share the matrix (row sharding keeps bits).  D % 4 == 0, 16-byte aligned
+ * X / Y rows.  gmr_spmm_blocked_plan_set_values re-reads `val` (same sparsity pattern, new values).
+ * stats[8] = {blocks, block_cols, tiles, segments, long segments, slots, small / big reduce entries}.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct gmr_spmm_bplan gmr_spmm_bplan_t;
+
+int gmr_spmm_blocked_plan_create(gmr_spmm_bplan_t** plan, const int32_t* rowptr, const int32_t* col, const float* val,
+                                 int64_t n_rows, int64_t n_cols, int64_t block_cols, void* stream);
+int gmr_spmm_blocked_plan_set_values(gmr_spmm_bplan_t* plan, const float* val, void* stream);
+int gmr_spmm_blocked_plan_destroy(gmr_spmm_bplan_t* plan);
+int gmr_spmm_blocked_plan_stats(const gmr_spmm_bplan_t* plan, int64_t* stats /* [8] */);
+int64_t gmr_spmm_blocked_workspace_bytes(const gmr_spmm_bplan_t* plan, int32_t D);
+int gmr_spmm_blocked_f32(const gmr_spmm_bplan_t* plan, const float* X, int64_t ldx, float* Y, int64_t ldy, int32_t D,
+                         float alpha, float beta, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Same product, with the result rows additionally PUSHED to peer buffers (fused all-gather of the
  * row-sharded layer output over NVLink peer memory): rank-local rows [0, n_rows) of this shard are
  * written to y_peers[p] + (row_offset + r) * ldy for every p in [0, n_peers).  y_peers is a
