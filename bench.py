@@ -1,19 +1,30 @@
-"""Contract benchmark of the hot path: DiffMM graph propagation + fused full-sort evaluation.
+"""Contract benchmark of the hot path: graph propagation + fused full-sort evaluation.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload scaled|baby|sports|clothing]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload scaled|baby|vbpr_baby|genrecv1_sports|ld4mrec_clothing|...]
     python bench.py --impl reference ...      # the CPU restatement of the reference on the host cores
 
-A STEP is one complete pass of the hot path over the synthetic workload: propagation (`forward_MM`:
-projections + every SpMM, never cached across steps), fused score + train-history mask + top-K over
-ALL eval users, hit matrix + Recall/NDCG/Precision/MAP.  `value` = eval users per second of the whole
-job (all ranks), inputs resident in HBM; `e2e` = the same through the public Trainer/evaluator API
-with the step's inputs (eval users, mask CSR, ground-truth CSR) copied from pinned host memory and
+A STEP is one complete pass of the hot path over the synthetic workload: propagation (never cached across steps),
+fused score + train-history mask + top-K over ALL eval users, hit matrix + Recall/NDCG/Precision/MAP.  `value` = eval
+users per second of the whole job (all ranks), inputs resident in HBM; `e2e` = the same through the public
+Trainer/evaluator API with the step's inputs (eval users, mask CSR, ground-truth CSR) copied from pinned host memory and
 the metric vector read back inside the timed region.  One JSON line on stdout (rank 0).
 
-Default workload: BASELINE.json configs[4] -- the 1M-user x 500k-item x 50M-interaction shape the
-metric is quoted on "at 1/2/4/8 B200" (it fits one GPU; operands exceed the L2, so no flush is
-needed).  Total work is fixed as N grows ("scaling": "strong").  The Baby-shaped DiffMM numbers
-(configs[1]) ride along under "workloads".
+Default workload: BASELINE.json configs[4] -- DiffMM at the 1M-user x 500k-item x 50M-interaction shape the metric is
+quoted on "at 1/2/4/8 B200" (it fits one GPU; operands exceed the L2, so no flush is needed).  Total work is fixed as N
+grows ("scaling": "strong").  The other BASELINE configs ride along under "workloads" at N = 1: DiffMM Baby (configs[1]),
+VBPR Baby (configs[0]), GenRecV1 Sports (configs[2]; also runnable as the main workload at --gpus 2/4) and LD4MRec
+Clothing (configs[3]).
+
+Besides the contract keys the line carries
+  * "parity": the GPU arm's top-K and metric partial sums for the first 4,096 eval users of the HEADLINE run compared
+    with what the CPU restatement of the reference returns for the same users (tie-aware, tests/parity.py rules); the
+    process exits non-zero when it fails.  With several ranks, rank 0 compares the sharded path with the single-GPU path
+    (bit-exact);
+  * "score_regimes" / "roofline_score": the fused scoring kernel on the model's own (norm-skewed) embeddings AND on
+    flat-norm embeddings of the same shape, where the Cauchy-Schwarz early stop cannot prune: the tensor roofline is
+    quoted on executed flops of the flat-norm run;
+  * "gpu_library_baseline": the reference's own GPU path (torch.sparse.mm / cuSPARSE, cuBLAS matmul, index_put_,
+    torch.topk per 4,096-user batch) on the same inputs and the same GPU, per operator.
 """
 import argparse
 import json
@@ -29,9 +40,25 @@ sys.path.insert(0, REPO)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-WORKLOAD_NAMES = {"scaled": "diffmm_scaled_1Mx500k_50M_top50", "baby": "diffmm_baby_19445x7050_160k_top50",
-                  "sports": "diffmm_sports_35598x18357_296k_top50", "clothing": "diffmm_clothing_39387x23033_278k_top50",
-                  "toy": "diffmm_toy_300x120_top50"}
+# name -> (model, shape, label)
+WORKLOADS = {
+    "scaled": ("DiffMM", "scaled", "diffmm_scaled_1Mx500k_50M_top50"),
+    "baby": ("DiffMM", "baby", "diffmm_baby_19445x7050_160k_top50"),
+    "sports": ("DiffMM", "sports", "diffmm_sports_35598x18357_296k_top50"),
+    "clothing": ("DiffMM", "clothing", "diffmm_clothing_39387x23033_278k_top50"),
+    "toy": ("DiffMM", "toy", "diffmm_toy_300x120_top50"),
+    "vbpr_baby": ("VBPR", "baby", "vbpr_baby_19445x7050_160k_top50"),
+    "genrecv1_sports": ("GenRecV1", "sports", "genrecv1_sports_35598x18357_296k_top50"),
+    "ld4mrec_clothing": ("LD4MRec", "clothing", "ld4mrec_clothing_39387x23033_278k_top50"),
+}
+PROPAGATION = {
+    "DiffMM": "DiffMM forward_MM (GenMMRec/src/models/diffmm.py:129-169)",
+    "VBPR": "VBPR forward: item_linear(cat(t, v)) (GenMMRec/src/models/vbpr.py:69-75)",
+    "GenRecV1": "GenRecV1 content embedding: user_item_GCN x 2 (GenMMRec/src/models/genrecv1.py:255-264,335-341)",
+    "LD4MRec": "LD4MRec CNet hidden states + output_proj (GenMMRec/src/models/ld4mrec.py:36,54,346-391)",
+}
+PARITY_USERS = 4096
+TIE_TOL, EMB_TOL, METRIC_TOL = 2e-5, 1e-5, 1e-6   # tests/parity.py
 
 
 def load_peaks():
@@ -100,6 +127,23 @@ class ClockSampler(object):
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def time_cuda(fn, iters=3, warmup=1):
+    """Median CUDA-event time of fn() in ms (synchronised on both sides)."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b))
+    ms.sort()
+    return ms[len(ms) // 2]
+
+
 # --------------------------------------------------------------------------------------------------
 # the GPU arm
 # --------------------------------------------------------------------------------------------------
@@ -140,50 +184,68 @@ class HostInputs(object):
         return self.eval_len_list
 
 
-def run_gpu(args):
+class LoaderHead(object):
+    """The first n eval users of a loader (views of its device tensors): the sample the parity check scores."""
+
+    def __init__(self, loader, n):
+        n = min(n, int(loader.eval_u.numel()))
+        self.n = n
+        self.eval_u = loader.eval_u[:n].contiguous()
+        self.mask_rowptr = loader.mask_rowptr[:n + 1].contiguous()
+        self.mask_items = loader.mask_items
+        self.gt_rowptr = loader.gt_rowptr[:n + 1].contiguous()
+        self.gt_items = loader.gt_items
+        self.eval_len_list = np.asarray(loader.eval_len_list)[:n]
+
+    def get_eval_len_list(self):
+        return self.eval_len_list
+
+
+def run_gpu(args, workload, steps, warmup, main=True):
+    """Time one workload.  Returns (json dict on rank 0, context dict)."""
     import torch.distributed as dist
 
     from genmmrec_b200 import ops
     from genmmrec_b200.common.trainer import Trainer
     from genmmrec_b200.workload import Workload
 
+    model_name, shape, label = WORKLOADS[workload]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     peaks = load_peaks()
 
     t_setup = time.time()
-    wl = Workload("DiffMM", args.workload, dev, overrides={"score_precision": args.precision})
+    wl = Workload(model_name, shape, dev, overrides={"score_precision": args.precision})
     model, cfg = wl.model, wl.config
     trainer = Trainer(cfg, model)
     k = max(cfg["topk"])
     full_loader = wl.valid
     sharded = None
     if world > 1:
-        from genmmrec_b200.dist import ShardedDiffMM, shard_eval_by_user_block
-        sharded = ShardedDiffMM(model)
+        from genmmrec_b200.dist import ShardedDiffMM, shard_eval_by_user_block, sharded_genrecv1
+        if model_name == "DiffMM":
+            sharded = ShardedDiffMM(model)
+        elif model_name == "GenRecV1":
+            sharded = sharded_genrecv1(model)
+        else:
+            raise SystemExit("workload %s has no multi-GPU form (row-sharded propagation exists for DiffMM and GenRecV1)" % workload)
         loader = shard_eval_by_user_block(full_loader, sharded.u0, sharded.u1)
     else:
         loader = full_loader
     n_eval_total = int(full_loader.eval_u.numel())
     host_in = HostInputs(loader, dev)
     sums_host = torch.empty((4, k), dtype=torch.float64).pin_memory()
-    adj = model.norm_adj
     l2_bytes = torch.cuda.get_device_properties(dev).L2_cache_size
-    operand_bytes = adj.full.algorithmic_bytes(cfg["embedding_size"])
-    need_flush = operand_bytes < 2 * l2_bytes
+    need_flush = shape != "scaled"   # the Amazon shapes are L2-resident (operands of 16-36 MB)
     flush_buf = torch.empty(max(2 * l2_bytes, 1 << 28), dtype=torch.uint8, device=dev) if need_flush else None
     torch.cuda.synchronize()
     setup_s = time.time() - t_setup
 
     def hot_path(inputs):
         """propagation (uncached) -> fused score/mask/top-K -> hits + metric sums."""
-        if sharded is not None:  # row-sharded propagation (fused SpMM + all-gather), user-block sharded eval
+        if sharded is not None:  # row-sharded propagation (peer-store all-gather), user-block sharded eval
             ue, ie = sharded.eval_factors()
             ids, _ = ops.score_mask_topk(ue.contiguous(), ie.contiguous(), k, users=inputs.eval_u,
                                          mask_rowptr=inputs.mask_rowptr, mask_items=inputs.mask_items,
@@ -192,16 +254,16 @@ def run_gpu(args):
             model.invalidate_cache()
             ids, _ = trainer.topk_all(inputs)
         sums, _ = trainer.evaluator.metric_sums(ids, inputs)
-        return sums
+        return sums, ids
 
     def step_resident():
-        sums = hot_path(loader)
+        sums, _ = hot_path(loader)
         if world > 1:
             dist.all_reduce(sums)
         return sums
 
     def enqueue_e2e():
-        sums = hot_path(host_in.upload())
+        sums, _ = hot_path(host_in.upload())
         if world > 1:
             dist.all_reduce(sums)
         sums_host.copy_(sums, non_blocking=True)
@@ -223,8 +285,8 @@ def run_gpu(args):
     use_graph = (not args.no_graph) and (world == 1 or os.environ.get("GMR_GRAPH_MULTI", "1") == "1")
     graph_state = {"failed": False}
 
-    def timed(fn, steps, warmup, profile=False, graph=False, sync_each=False):
-        for _ in range(warmup):
+    def timed(fn, n_steps, n_warm, profile=False, graph=False, sync_each=False):
+        for _ in range(n_warm):
             fn()
         barrier()
         run = fn
@@ -244,7 +306,7 @@ def run_gpu(args):
         launches0 = ops.LAUNCHES
         evs = []
         t0 = time.perf_counter()
-        for _ in range(steps):
+        for _ in range(n_steps):
             if flush_buf is not None:
                 flush_buf.fill_(1)  # L2 flush between timed iterations (outside the per-step events)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -265,16 +327,16 @@ def run_gpu(args):
         return ms, wall, ops.LAUNCHES - launches0, prof
 
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and main:
         sampler.start()
-    # timed region: the step replayed from a CUDA graph (single GPU; eager launches otherwise).  Per-kernel durations
+    # timed region: the step replayed from a CUDA graph (eager launches if the capture is refused).  Per-kernel durations
     # and the launch count come from a separate eager pass with CUDA events around every operator.
-    ms_total, wall, launches, _ = timed(step_resident, args.steps, args.warmup, graph=use_graph)
-    clocks = sampler.stop() if rank == 0 else None
-    ms_eager, _, launches, prof = timed(step_resident, args.steps, 1, profile=True)
-    ms_e2e, _, _, _ = timed(enqueue_e2e if use_graph else step_e2e, args.steps, max(1, args.warmup // 2), graph=use_graph,
+    ms_total, wall, launches, _ = timed(step_resident, steps, warmup, graph=use_graph)
+    clocks = sampler.stop() if (rank == 0 and main) else None
+    ms_eager, _, launches, prof = timed(step_resident, steps, 1, profile=True)
+    ms_e2e, _, _, _ = timed(enqueue_e2e if use_graph else step_e2e, steps, max(1, warmup // 2), graph=use_graph,
                             sync_each=use_graph)
-    if os.environ.get("GMR_PROFILE_STEP"):  # ncu --profile-from-start off: exactly one resident step is captured
+    if main and os.environ.get("GMR_PROFILE_STEP"):  # ncu --profile-from-start off: exactly one resident step is captured
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStart()
         step_resident()
@@ -282,7 +344,7 @@ def run_gpu(args):
         torch.cuda.cudart().cudaProfilerStop()
     result_dict, raw = trainer.evaluator.finalize(step_resident(), n_eval_total)
 
-    # ---- per-kernel durations from the CUDA events recorded inside the timed region ----------------
+    # ---- per-kernel durations from the CUDA events recorded inside the eager pass ------------------
     per = {}
     for name, meta, a, b in prof:
         key = name if name != "spmm" else "spmm[%dx%d,nnz=%d,D=%d]" % (meta["rows"], meta["cols"], meta["nnz"], meta["d"])
@@ -291,10 +353,11 @@ def run_gpu(args):
     kernels = {}
     for key, e in per.items():
         avg = float(np.mean(e["ms"]))
-        kk = {"avg_ms": avg, "launches_per_step": len(e["ms"]) / args.steps}
+        kk = {"avg_ms": avg, "launches_per_step": len(e["ms"]) / steps}
         if e["op"] == "spmm":
             kk["alg_GBs"] = e["meta"]["alg_bytes"] / avg / 1e6
             kk["gather_GBs"] = e["meta"]["nnz"] * (8 + 4 * e["meta"]["d"]) / avg / 1e6
+            kk["kernel"] = e["meta"].get("kernel", "row")
         if e["op"] == "score_topk":
             kk["alg_TFLOPs"] = e["meta"]["flops"] / avg / 1e9
         if e["op"] == "dense_projections":
@@ -302,11 +365,11 @@ def run_gpu(args):
             kk["TFLOPs"] = e["meta"]["flops"] / avg / 1e9
             kk["GBs"] = e["meta"]["bytes"] / avg / 1e6
         kernels[key] = kk
-    step_ms = ms_total / args.steps
+    step_ms = ms_total / steps
     for kk in kernels.values():
         kk["share_of_step"] = kk["avg_ms"] * kk["launches_per_step"] / step_ms
     spmm_keys = [kname for kname, e in per.items() if e["op"] == "spmm"]
-    big_spmm = max(spmm_keys, key=lambda kname: per[kname]["meta"]["alg_bytes"])
+    big_spmm = max(spmm_keys, key=lambda kname: per[kname]["meta"]["alg_bytes"]) if spmm_keys else None
     prop_ms = step_ms - sum(kernels[kname]["avg_ms"] * kernels[kname]["launches_per_step"]
                             for kname in kernels if per[kname]["op"] in ("score_topk", "hits_metrics"))
     traffic = load_traffic()
@@ -319,19 +382,8 @@ def run_gpu(args):
                 "algorithmic_bytes_per_launch": per[kname]["meta"]["alg_bytes"],
                 "peak_source": peaks["source"] + " copy bandwidth",
                 "note": "algorithmic bytes = CSR read once + X read once + Y written once (SURVEY.md 8d); gather_model_GBs "
-                        "counts every gathered embedding row (what the L2 actually serves)"}
-
-    def tensor_roofline():
-        kk = kernels["score_topk"]
-        return {"kernel": "score_mask_topk (%s)" % args.precision, "bound": "tensor", "achieved": kk["alg_TFLOPs"],
-                "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": kk["alg_TFLOPs"] / peaks["bf16_tflops_sustained"],
-                "traffic": traffic.get("score_topk"), "avg_ms": kk["avg_ms"], "share_of_step": kk["share_of_step"],
-                "peak_source": peaks["source"] + " bf16 sustained (kernel timed inside a long step)",
-                "note": "flops = 2*U*I*D of the reference's dense matmul.  The tc mode sweeps items in descending-norm order "
-                        "and stops a 256-user group as soon as Cauchy-Schwarz rules out every remaining item, so it executes "
-                        "only the tiles that can matter: on popularity-skewed embeddings `achieved` exceeds the tensor peak "
-                        "because most of the dense product is provably irrelevant and never computed (exact results; "
-                        "GMR_TC_DEBUG=3 forces the full sweep).  tc_split issues 3x the flops; fp32 runs on CUDA cores."}
+                        "counts every gathered embedding row (what the L2 -> SM path actually serves: measured ceiling "
+                        "16.5 TB/s for an L2-resident table, 8.9 TB/s at 256 MB, profiles/r02_spmm_table_sweep.log)"}
 
     def proj_roofline():
         kk = kernels["dense_projections"]
@@ -343,39 +395,184 @@ def run_gpu(args):
                 "note": "algorithmic bytes = feature matrices read once + outputs written once; 3 TF32 MMAs per product term"}
 
     # `roofline` describes the single KERNEL of ours that holds the largest share of the step.  score_topk is a
-    # sequence of nine launches (operand prep, two sweeps, checkpoint, finalise, fp32 redo; the largest of them is
-    # smaller than the SpMMs, profiles/r01_ncu_launches_step_*.csv) and is described by `roofline_score`.
+    # sequence of launches (operand prep, two sweeps, checkpoint, finalise, fp32 redo) described by `roofline_score`.
     single = [kname for kname in kernels if per[kname]["op"] in ("spmm", "dense_projections")]
-    dominant = max(single, key=lambda kname: kernels[kname]["avg_ms"])
-    roofline = proj_roofline() if per[dominant]["op"] == "dense_projections" else hbm_roofline(dominant)
-    roofline_spmm = hbm_roofline(big_spmm)
-    roofline_score = tensor_roofline()
+    roofline = roofline_spmm = None
+    if single:
+        dominant = max(single, key=lambda kname: kernels[kname]["avg_ms"])
+        roofline = proj_roofline() if per[dominant]["op"] == "dense_projections" else hbm_roofline(dominant)
+    if big_spmm is not None:
+        roofline_spmm = hbm_roofline(big_spmm)
 
     out = None
     if rank == 0:
         out = {
             "metric": "full_sort_eval_users_per_s", "value": n_eval_total / step_ms * 1e3, "unit": "users/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD_NAMES[args.workload], "propagation": "DiffMM forward_MM (GenMMRec/src/models/diffmm.py:129-169)", "n_users": wl.n_users,
+            "config": {"workload": label, "propagation": PROPAGATION[model_name], "n_users": wl.n_users,
                        "n_items": wl.n_items, "nnz_train": wl.nnz_train, "eval_users": n_eval_total, "topk": k,
                        "embedding_size": cfg["embedding_size"], "n_layers": cfg["n_layers"],
                        "score_precision": args.precision,
                        "launch": "CUDA graph replay of the whole step" if (use_graph and not graph_state["failed"]) else "eager launches",
-                       "parallelism": ("row-sharded propagation (push-SpMM all-gather) + user-block sharded eval, x%d" % world)
+                       "parallelism": ("row-sharded propagation (each rank stores its row block into every peer's replica "
+                                       "over NVLink peer memory) + user-block sharded eval, x%d" % world)
                        if world > 1 else "single GPU",
                        "l2": ("L2 flushed between timed steps (operands fit the %d MB L2)" % (l2_bytes >> 20)) if need_flush
-                       else ("operands (%.0f MB per SpMM) exceed the %d MB L2; no flush" % (operand_bytes / 1e6, l2_bytes >> 20))},
-            "propagation_step_ms": prop_ms, "spmm_hbm_GBs": kernels[big_spmm]["alg_GBs"],
-            "roofline": roofline, "roofline_spmm": roofline_spmm, "roofline_score": roofline_score,
+                       else ("operands exceed the %d MB L2; no flush" % (l2_bytes >> 20))},
+            "propagation_step_ms": prop_ms,
+            "spmm_hbm_GBs": kernels[big_spmm]["alg_GBs"] if big_spmm is not None else None,
+            "roofline": roofline, "roofline_spmm": roofline_spmm,
             "roofline_proj": proj_roofline() if "dense_projections" in kernels else None, "kernels": kernels,
-            "e2e": {"value": n_eval_total / (ms_e2e / args.steps) * 1e3, "unit": "users/s",
+            "e2e": {"value": n_eval_total / (ms_e2e / steps) * 1e3, "unit": "users/s",
                     "h2d_bytes_per_step": host_in.bytes * world, "d2h_bytes_per_step": int(sums_host.numel() * 8),
-                    "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "eager_ms_per_step": ms_eager / args.steps, "clocks": clocks, "wall_s_timed_region": wall, "setup_s": setup_s,
+                    "ms_per_step": ms_e2e / steps},
+            "gpu_launches": launches, "eager_ms_per_step": ms_eager / steps, "clocks": clocks, "wall_s_timed_region": wall, "setup_s": setup_s,
             "metrics": result_dict,
         }
-    return out, wl, trainer, full_loader
+    ctx = {"wl": wl, "trainer": trainer, "loader": full_loader, "local_loader": loader, "sharded": sharded, "k": k,
+           "hot_path": hot_path, "model_name": model_name, "peaks": peaks, "kernels": kernels, "world": world, "rank": rank}
+    return out, ctx
+
+
+# --------------------------------------------------------------------------------------------------
+# scoring regimes: the model's own embeddings (norm-skewed: the early stop prunes) and flat norms (full sweep)
+# --------------------------------------------------------------------------------------------------
+
+
+def score_regimes(ctx, args):
+    """Time the fused score + mask + top-K operator on (a) the propagated embeddings of the workload and (b) flat-norm
+    embeddings of the same shape (unit-norm Gaussian rows: Cauchy-Schwarz cannot prune, every item tile is multiplied),
+    with the executed tile counts.  The tensor roofline is quoted on the EXECUTED flops of (b)."""
+    from genmmrec_b200 import ops
+
+    wl, loader, k, peaks = ctx["wl"], ctx["loader"], ctx["k"], ctx["peaks"]
+    model = wl.model
+    dev = loader.eval_u.device
+    with torch.no_grad():
+        eu, rows, ei, bias = model.eval_factors(loader.eval_u)
+    eu, ei = eu.contiguous(), ei.contiguous()
+    b, i, d = int(rows.numel()), int(ei.shape[0]), int(ei.shape[1])
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234)
+    fu = torch.nn.functional.normalize(torch.randn(eu.shape, device=dev, generator=g), dim=1)
+    fi = torch.nn.functional.normalize(torch.randn(ei.shape, device=dev, generator=g), dim=1)
+    n_groups, tiles_full = (b + 255) // 256, (i + 127) // 128
+    out = {}
+    for name, (u, it) in (("model_embeddings", (eu, ei)), ("flat_norms", (fu, fi))):
+        fn = lambda: ops.score_mask_topk(u, it, k, users=rows, bias=bias, mask_rowptr=loader.mask_rowptr,
+                                         mask_items=loader.mask_items, precision=args.precision, return_scores=False)
+        ms = time_cuda(fn, iters=3, warmup=1)
+        e = {"ms": ms, "users_per_s": b / ms * 1e3, "dense_TFLOPs": 2.0 * b * i * d / ms / 1e9,
+             "item_norm_max_over_median": float(it.norm(dim=1).max() / it.norm(dim=1).median())}
+        if args.precision == "tc":
+            os.environ["GMR_SCREEN_STATS"] = "1"   # counters cost time: separate, untimed call
+            fn()
+            st = ops.last_tc_stats()
+            os.environ.pop("GMR_SCREEN_STATS", None)
+            tiles = float(st.get("tiles_swept", 0))
+            e.update({"tiles_swept_per_256_users": tiles / n_groups, "tiles_full_sweep": tiles_full,
+                      "rescored_per_row": st.get("rescored", 0) / b, "fp32_redo_rows": ops.last_tc_fallback_rows(),
+                      "executed_TFLOPs": tiles * 256 * 128 * 2.0 * d / ms / 1e9})
+        out[name] = e
+    flat = out["flat_norms"]
+    ach = flat.get("executed_TFLOPs", flat["dense_TFLOPs"])
+    roofline = {"kernel": "score_mask_topk (%s), flat-norm embeddings (full sweep)" % args.precision, "bound": "tensor",
+                "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": ach / peaks["bf16_tflops_sustained"], "traffic": load_traffic().get("score_topk"),
+                "avg_ms": flat["ms"], "peak_source": peaks["source"] + " bf16 sustained",
+                "note": "executed flops = item tiles actually multiplied x 256 users x 128 items x 2 D, on flat-norm inputs "
+                        "where the norm-ordered early stop cannot prune.  On the workload's own embeddings (score_regimes."
+                        "model_embeddings) the sweep stops after tiles_swept_per_256_users of tiles_full_sweep tiles because "
+                        "Cauchy-Schwarz rules the rest out (exact results, checked under 'parity'); that run is bound by the "
+                        "per-row SIMT bookkeeping, not by the tensor pipe."}
+    return out, roofline
+
+
+# --------------------------------------------------------------------------------------------------
+# the reference's own GPU path: PyTorch library kernels on the same inputs, same GPU
+# --------------------------------------------------------------------------------------------------
+
+
+def gpu_library_baseline(ctx, batch_users=4096, n_batches=3):
+    """What the reference does on a GPU: torch.sparse.mm on its uncoalesced COO graphs (cuSPARSE behind a
+    per-call coalesce), cuBLAS matmul, index_put_ and torch.topk per eval_batch_size users, with forward_MM re-run for
+    every batch (GenMMRec/src/models/diffmm.py:276, common/trainer.py:379-387).  DiffMM only."""
+    wl, loader, k = ctx["wl"], ctx["loader"], ctx["k"]
+    m, cfg = wl.model, wl.config
+    nu = wl.n_users
+
+    def coo(gr):
+        return gr.to_torch_coo()   # uncoalesced, row-major: what the reference's builders hand to torch.sparse.mm
+
+    adj, img, txt = coo(m.norm_adj.full), coo(m.image_UI_matrix), coo(m.text_UI_matrix)
+    w = torch.softmax(m.modal_weight.detach(), dim=0)
+    lrelu = torch.nn.functional.leaky_relu
+
+    def forward_mm():   # GenMMRec/src/models/diffmm.py:129-169, literally, on library kernels
+        ifeat = lrelu(torch.mm(m.v_feat, m.image_trans.detach()), 0.2)
+        tfeat = lrelu(torch.mm(m.t_feat, m.text_trans.detach()), 0.2)
+        u0, i0 = m.uEmbeds.detach(), m.iEmbeds.detach()
+
+        def branch(m_adj, feats):
+            e_adj = torch.sparse.mm(m_adj, torch.cat([u0, i0]))
+            e = torch.sparse.mm(adj, torch.cat([u0, torch.nn.functional.normalize(feats)]))
+            e_ = torch.sparse.mm(adj, torch.cat([e[:nu], i0]))
+            return (e + e_) + m.ris_adj_lambda * e_adj
+
+        modal = w[0] * branch(img, ifeat) + w[1] * branch(txt, tfeat)
+        lst = [modal]
+        for _ in range(m.gnn_layer):
+            lst.append(torch.sparse.mm(adj, lst[-1]))
+        e = sum(lst) + m.ris_lambda * torch.nn.functional.normalize(modal)
+        return e[:nu], e[nu:]
+
+    with torch.no_grad():
+        x = torch.cat([m.uEmbeds.detach(), m.iEmbeds.detach()])
+        spmm_coo_ms = time_cuda(lambda: torch.sparse.mm(adj, x), iters=3)
+        adj_csr = adj.coalesce().to_sparse_csr()
+        spmm_csr_ms = time_cuda(lambda: torch.sparse.mm(adj_csr, x), iters=3)
+        fwd_ms = time_cuda(forward_mm, iters=2)
+        ue, ie = forward_mm()
+        n_eval = int(loader.eval_u.numel())
+        b = min(batch_users, n_eval)
+        batch_ms, parts = [], {"matmul_ms": [], "index_put_ms": [], "topk_ms": []}
+        for j in range(min(n_batches, (n_eval + b - 1) // b)):
+            users = loader.eval_u[j * b:(j + 1) * b]
+            rp = loader.mask_rowptr[j * b:j * b + users.numel() + 1]
+            items = loader.mask_items[int(rp[0]):int(rp[-1])].long()
+            rowsb = torch.repeat_interleave(torch.arange(users.numel(), device=users.device), rp[1:] - rp[:-1])
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            torch.cuda.synchronize()
+            evs[0].record()
+            scores = torch.matmul(ue[users], ie.transpose(0, 1))
+            evs[1].record()
+            scores[rowsb, items] = -1e10
+            evs[2].record()
+            _, idx = torch.topk(scores, k, dim=-1)
+            evs[3].record()
+            torch.cuda.synchronize()
+            if j > 0 or n_batches == 1:   # first batch warms the allocator
+                parts["matmul_ms"].append(evs[0].elapsed_time(evs[1]))
+                parts["index_put_ms"].append(evs[1].elapsed_time(evs[2]))
+                parts["topk_ms"].append(evs[2].elapsed_time(evs[3]))
+                batch_ms.append(evs[0].elapsed_time(evs[3]))
+            del scores, idx
+    per_batch = float(np.mean(batch_ms))
+    n_b = (n_eval + b - 1) // b
+    total_ref_ms = n_b * (fwd_ms + per_batch)
+    total_cached_ms = fwd_ms + n_b * per_batch
+    return {"kind": "PyTorch library kernels on the same GPU and inputs (cuSPARSE / cuBLAS / torch.topk); the reference's "
+                    "Python hit loop + numpy metrics are NOT included",
+            "torch": torch.__version__, "batch_users": b, "batches_timed": len(batch_ms), "batches_total": n_b,
+            "spmm_norm_adj_coo_uncoalesced_ms": spmm_coo_ms, "spmm_norm_adj_csr_ms": spmm_csr_ms,
+            "spmm_norm_adj_coo_alg_GBs": (adj._nnz() * 8 + (adj.shape[0] + 1) * 4 + 2 * x.numel() * 4) / spmm_coo_ms / 1e6,
+            "spmm_norm_adj_csr_alg_GBs": (adj._nnz() * 8 + (adj.shape[0] + 1) * 4 + 2 * x.numel() * 4) / spmm_csr_ms / 1e6,
+            "forward_MM_ms": fwd_ms, "per_batch_ms": per_batch, "per_batch_parts": {kk: float(np.mean(v)) for kk, v in parts.items()},
+            "users_per_s_as_the_reference_runs_it": n_eval / total_ref_ms * 1e3,
+            "users_per_s_with_propagation_cached": n_eval / total_cached_ms * 1e3,
+            "sample": "forward_MM timed in full; %d of %d score/mask/top-K batches timed and extrapolated linearly"
+                      % (len(batch_ms), n_b)}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -384,26 +581,34 @@ def run_gpu(args):
 
 
 class CpuReference(object):
-    """The reference's own evaluation step restated on CPU tensors (oracle/ref_port.py): per batch of
-    `eval_batch_size` users it re-runs forward_MM (models/diffmm.py:276), multiplies, masks, takes
-    torch.topk and runs the Python hit loop + numpy metrics (common/trainer.py:379-388,
-    utils/topk_evaluator.py:107-120)."""
+    """The reference's own evaluation step restated on CPU tensors (oracle/ref_port.py): per batch of `eval_batch_size`
+    users it re-runs the model's forward (models/diffmm.py:276, vbpr.py:100-106, genrecv1.py:417-427,
+    ld4mrec.py:346-391), multiplies, masks, takes torch.topk and runs the Python hit loop + numpy metrics
+    (common/trainer.py:379-388, utils/topk_evaluator.py:107-120)."""
 
-    def __init__(self, wl, loader, batch_users):
+    def __init__(self, wl, loader, batch_users, model_name="DiffMM"):
         from oracle import ref_port as rp
         self.rp = rp
+        self.name = model_name
         m = wl.model
         self.cfg = wl.config
-        self.nu = wl.n_users
+        self.nu, self.ni = wl.n_users, wl.n_items
 
         def coo(g):
             t = g.to_torch_coo()
             return torch.sparse_coo_tensor(t._indices().cpu(), t._values().cpu(), t.shape)  # uncoalesced, as shipped
 
-        self.adj = coo(m.norm_adj.full)
-        self.img_adj, self.txt_adj = coo(m.image_UI_matrix), coo(m.text_UI_matrix)
         self.p = {k: v.detach().cpu() for k, v in m.state_dict().items()}
-        self.v_feat, self.t_feat = m.v_feat.cpu(), m.t_feat.cpu()
+        if model_name == "DiffMM":
+            self.adj = coo(m.norm_adj.full)
+            self.img_adj, self.txt_adj = coo(m.image_UI_matrix), coo(m.text_UI_matrix)
+        elif model_name == "GenRecV1":
+            self.adj, self.img_adj = coo(m.norm_adj.full), coo(m.image_UI_matrix)
+        elif model_name == "LD4MRec":
+            self.r = coo(m.R)
+            self.user_svd, self.user_mm = m.user_svd_emb.cpu(), m.user_mm_emb.cpu()
+        if m.v_feat is not None:
+            self.v_feat, self.t_feat = m.v_feat.cpu(), m.t_feat.cpu()
         b = min(batch_users, int(loader.eval_u.numel()))
         self.b = b
         self.users = loader.eval_u[:b].cpu()
@@ -416,39 +621,128 @@ class CpuReference(object):
         self.gt_len = np.diff(g_rp)
         self.k = max(self.cfg["topk"])
         self.parts = {}
+        self.last = {}
+
+    def _scores(self):
+        rp, cfg, p = self.rp, self.cfg, self.p
+        if self.name == "DiffMM":
+            ue, ie = rp.diffmm_forward_mm(p, self.adj, self.img_adj, self.txt_adj, self.v_feat, self.t_feat, self.nu,
+                                          cfg["n_layers"], cfg["ris_lambda"], cfg["ris_adj_lambda"])
+        elif self.name == "VBPR":
+            ue, ie = rp.vbpr_forward(p, self.t_feat, self.v_feat)
+        elif self.name == "GenRecV1":
+            c = rp.genrecv1_content(p, self.adj, self.img_adj, self.nu, cfg["n_layers"])
+            ue, ie = c[:self.nu], c[self.nu:]
+        elif self.name == "LD4MRec":
+            x_in = torch.index_select(self.r, 0, self.users).to_dense()   # [B, n_items] history rows (ld4mrec.py:357-359)
+            h = rp.ld4mrec_hidden(p, x_in, self.user_svd[self.users], self.user_mm[self.users], cfg["cnet_n_layers"])
+            t1 = time.perf_counter()
+            return None, None, torch.addmm(p["cnet.output_proj.bias"], h, p["cnet.output_proj.weight"].t()), t1
+        else:
+            raise ValueError(self.name)
+        t1 = time.perf_counter()
+        return ue, ie, torch.matmul(ue[self.users], ie.transpose(0, 1)), t1
 
     def step(self):
         rp, cfg = self.rp, self.cfg
         t0 = time.perf_counter()
         with torch.no_grad():
-            ue, ie = rp.diffmm_forward_mm(self.p, self.adj, self.img_adj, self.txt_adj, self.v_feat, self.t_feat, self.nu,
-                                          cfg["n_layers"], cfg["ris_lambda"], cfg["ris_adj_lambda"])
-            t1 = time.perf_counter()
-            scores = torch.matmul(ue[self.users], ie.transpose(0, 1))
+            ue, ie, scores, t1 = self._scores()
             scores[self.mask[0], self.mask[1]] = -1e10
             _, idx = torch.topk(scores, self.k, dim=-1)
         t2 = time.perf_counter()
         hit = rp.hit_matrix(idx.numpy(), self.gt)
         raw = np.stack([rp.METRICS[mm.lower()](hit, self.gt_len) for mm in cfg["metrics"]], axis=0)
         t3 = time.perf_counter()
-        self.parts = {"forward_MM_s": t1 - t0, "score_mask_topk_s": t2 - t1, "hits_metrics_s": t3 - t2}
+        self.parts = {"forward_s": t1 - t0, "score_mask_topk_s": t2 - t1, "hits_metrics_s": t3 - t2}
+        self.last = {"idx": idx.numpy(), "raw": raw, "ue": ue, "ie": ie, "scores": scores}
         return t3 - t0, raw
 
 
-def cpu_baseline(wl, loader, steps=1, warmup=0, batch_users=4096):
+def cpu_baseline(wl, loader, steps=1, warmup=0, batch_users=4096, model_name="DiffMM"):
     cores = os.cpu_count()
     torch.set_num_threads(cores)
-    ref = CpuReference(wl, loader, batch_users)
+    ref = CpuReference(wl, loader, batch_users, model_name)
     for _ in range(warmup):
         ref.step()
     ts = [ref.step()[0] for _ in range(steps)]
     t = float(np.mean(ts))
     return {"value": ref.b / t, "unit": "users/s", "cores": cores, "kind": "port",
-            "sample": "one reference evaluation batch of %d users (incl. the forward_MM the reference re-runs per "
+            "sample": "one reference evaluation batch of %d users (incl. the model forward the reference re-runs per "
                       "batch, the [B, n_items] matmul, mask, torch.topk and the Python hit loop + numpy metrics); "
                       "users/s = batch / batch time, i.e. linear extrapolation over the %d eval users"
                       % (ref.b, int(loader.eval_u.numel())),
-            "seconds_per_batch": t, "parts": ref.parts}, ts
+            "seconds_per_batch": t, "parts": ref.parts}, ts, ref
+
+
+def parity_vs_cpu(ctx, ref):
+    """GPU arm vs the CPU restatement on the first `ref.b` eval users of the SAME run: propagated embeddings, top-K ids
+    (tie-aware: differing positions must name items whose fp64 scores are within TIE_TOL of the row's score scale) and the
+    unrounded metric vectors of those users."""
+    from genmmrec_b200 import ops
+
+    wl, loader, trainer, k = ctx["wl"], ctx["loader"], ctx["trainer"], ctx["k"]
+    model = wl.model
+    head = LoaderHead(loader, ref.b)
+    with torch.no_grad():
+        model.invalidate_cache()
+        ids, _ = trainer.topk_all(head)
+        sums, _ = trainer.evaluator.metric_sums(ids, head)
+    ids = ids.cpu().numpy()
+    got_raw = (sums / float(head.n)).cpu().numpy()           # rows: recall, ndcg, precision, map
+    order = {"recall": 0, "ndcg": 1, "precision": 2, "map": 3}
+    got_raw = np.stack([got_raw[order[m.lower()]] for m in wl.config["metrics"]], axis=0)
+    ref_ids, ref_raw = ref.last["idx"], ref.last["raw"]
+    diff_rows = np.flatnonzero((ids != ref_ids).any(axis=1))
+    out = {"against": "CPU restatement of the reference (oracle/ref_port.py), same users, same run",
+           "users": int(head.n), "rows_identical": int(head.n - diff_rows.size), "tie_tol": TIE_TOL}
+    if ref.last["ue"] is not None:
+        with torch.no_grad():
+            ue, ie = model.cached_propagate()
+        e_u = float((ue.cpu() - ref.last["ue"]).abs().max() / ref.last["ue"].abs().max())
+        e_i = float((ie.cpu() - ref.last["ie"]).abs().max() / ref.last["ie"].abs().max())
+        out["embedding_rel_err"] = max(e_u, e_i)
+    max_gap = 0.0
+    s_ref = ref.last["scores"].double().numpy()   # masked fp32 reference scores of the batch (CPU)
+    for r in diff_rows:
+        s = s_ref[r]
+        scale = np.abs(s[s > -1e9]).max()
+        gap = np.abs(s[ids[r]] - s[ref_ids[r]]).max() / scale
+        max_gap = max(max_gap, float(gap))
+    out["max_gap"] = max_gap
+    out["metric_max_abs"] = float(np.abs(got_raw - ref_raw).max())
+    # a row whose ranking differs inside the tie tolerance can move a hit across a cut-off: 1 / users per such row
+    metric_bound = METRIC_TOL + diff_rows.size / float(head.n)
+    out["ok"] = bool(max_gap <= TIE_TOL and out["metric_max_abs"] <= metric_bound and out.get("embedding_rel_err", 0.0) <= EMB_TOL)
+    return out
+
+
+def parity_sharded(ctx, args):
+    """Several ranks: this rank's sharded result against the single-GPU path of the same model replica, on the first
+    PARITY_USERS eval users of its block.  Ids must be identical; embeddings are reported (bit-identity expected)."""
+    from genmmrec_b200 import ops
+
+    wl, trainer, k, sharded, shard = ctx["wl"], ctx["trainer"], ctx["k"], ctx["sharded"], ctx["local_loader"]
+    model = wl.model
+    n = min(PARITY_USERS, int(shard.eval_u.numel()))
+    with torch.no_grad():
+        ue_s, ie_s = sharded.eval_factors()
+        ids_s, _ = ops.score_mask_topk(ue_s.contiguous(), ie_s.contiguous(), k, users=shard.eval_u[:n].contiguous(),
+                                       mask_rowptr=shard.mask_rowptr[:n + 1].contiguous(), mask_items=shard.mask_items,
+                                       precision=args.precision, return_scores=False)
+        model.invalidate_cache()
+        ue, ie = model.cached_propagate()
+        users_global = (shard.eval_u[:n] + sharded.u0).contiguous()
+        ids_1, _ = ops.score_mask_topk(ue.contiguous(), ie.contiguous(), k, users=users_global,
+                                       mask_rowptr=shard.mask_rowptr[:n + 1].contiguous(), mask_items=shard.mask_items,
+                                       precision=args.precision, return_scores=False)
+        emb_equal = bool(torch.equal(ue[sharded.u0:sharded.u1], ue_s) and torch.equal(ie, ie_s))
+        emb_err = max(float((ue[sharded.u0:sharded.u1] - ue_s).abs().max() / ue.abs().max()),
+                      float((ie - ie_s).abs().max() / ie.abs().max()))
+    same = int((ids_s == ids_1).all(dim=1).sum())
+    return {"against": "single-GPU path of the same model replica (rank 0's user block)", "users": n,
+            "rows_identical": same, "embeddings_bit_identical": emb_equal, "embedding_rel_err": emb_err,
+            "ok": bool(same == n and emb_err <= EMB_TOL)}
 
 
 def run_reference(args):
@@ -459,21 +753,22 @@ def run_reference(args):
         return None
     from genmmrec_b200.workload import Workload
 
+    model_name, shape, label = WORKLOADS[args.workload]
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
-    wl = Workload("DiffMM", args.workload, dev, overrides={"score_precision": "fp32"})  # same synthetic inputs
+    wl = Workload(model_name, shape, dev, overrides={"score_precision": "fp32"})  # same synthetic inputs
     budget = 240.0
-    base, _ = cpu_baseline(wl, wl.valid, steps=1, warmup=0)
+    base, _, _ = cpu_baseline(wl, wl.valid, steps=1, warmup=0, model_name=model_name)
     t1 = base["seconds_per_batch"]
     steps = max(1, min(args.steps, int(budget / t1) - 1))
     warm = 1 if args.warmup > 0 and (steps + 1) * t1 < budget else 0
-    base, ts = cpu_baseline(wl, wl.valid, steps=steps, warmup=warm)
+    base, ts, _ = cpu_baseline(wl, wl.valid, steps=steps, warmup=warm, model_name=model_name)
     k = max(wl.config["topk"])
     return {
         "impl": "reference", "metric": "full_sort_eval_users_per_s", "value": base["value"], "unit": "users/s",
         "n_gpus": world, "steps": args.steps, "steps_run": steps, "warmup": args.warmup, "warmup_run": warm + 1,
         "ms_per_step": base["seconds_per_batch"] * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAMES[args.workload], "propagation": "DiffMM forward_MM (GenMMRec/src/models/diffmm.py:129-169)", "n_users": wl.n_users,
+        "config": {"workload": label, "propagation": PROPAGATION[model_name], "n_users": wl.n_users,
                    "n_items": wl.n_items, "nnz_train": wl.nnz_train, "eval_users": wl.n_eval_users, "topk": k,
                    "embedding_size": wl.config["embedding_size"], "n_layers": wl.config["n_layers"]},
         "cpu_baseline": base,
@@ -491,13 +786,16 @@ def _claim_stdout():
     return os.fdopen(real, "w")
 
 
+EXTRA_WORKLOADS = ("baby", "vbpr_baby", "genrecv1_sports", "ld4mrec_clothing")
+
+
 def main():
     out_stream = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="scaled", choices=sorted(WORKLOAD_NAMES))
+    ap.add_argument("--workload", default="scaled", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("GMR_SCORE_PRECISION", "tc"), choices=["fp32", "tc", "tc_split"],
                     help="scoring path: tc = fp16 tcgen05 certified screen + exact fp32 re-score (default), tc_split = "
@@ -505,6 +803,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay of the step")
     ap.add_argument("--no-extra-workloads", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if not torch.cuda.is_available():
@@ -517,32 +816,69 @@ def main():
             out_stream.flush()
         return
 
-    out, wl, trainer, loader = run_gpu(args)
-    rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+
+    out, ctx = run_gpu(args, args.workload, args.steps, args.warmup, main=True)
+    model_name = ctx["model_name"]
+    failed = None
+    if world > 1:
+        par = parity_sharded(ctx, args)   # every rank runs it (the sharded forward is collective); rank 0 reports
+        if rank == 0:
+            out["parity"] = par
+            if not par["ok"]:
+                failed = "sharded path differs from the single-GPU path: %r" % (par,)
     if rank == 0:
+        if model_name in ("DiffMM", "VBPR", "GenRecV1") and args.precision == "tc":
+            try:
+                out["score_regimes"], out["roofline_score"] = score_regimes(ctx, args)
+            except Exception as e:  # diagnostics must not cost the headline line
+                out["score_regimes"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
-            base, _ = cpu_baseline(wl, loader, steps=1, warmup=0)
+            base, _, ref = cpu_baseline(ctx["wl"], ctx["loader"], steps=1, warmup=0, model_name=model_name)
             out["cpu_baseline"] = base
-        if world == 1 and not args.no_extra_workloads and args.workload != "baby":
-            del wl, trainer, loader
+            out["parity"] = parity_vs_cpu(ctx, ref)
+            if not out["parity"]["ok"]:
+                failed = "GPU arm differs from the CPU restatement of the reference: %r" % (out["parity"],)
+            del ref
+        if world == 1 and model_name == "DiffMM" and not args.no_library_baseline:
+            try:
+                out["gpu_library_baseline"] = gpu_library_baseline(ctx)
+            except Exception as e:
+                out["gpu_library_baseline"] = {"error": repr(e)}
+        if world == 1 and not args.no_extra_workloads and args.workload == "scaled":
+            del ctx
             torch.cuda.empty_cache()
-            sub = argparse.Namespace(**vars(args))
-            sub.workload, sub.steps, sub.warmup = "baby", 20, 5
-            o2, wl2, _, ld2 = run_gpu(sub)
-            extra = {k: o2[k] for k in ("value", "unit", "ms_per_step", "propagation_step_ms", "spmm_hbm_GBs", "e2e",
-                                        "gpu_launches", "metrics")}
-            extra["config"] = o2["config"]
-            extra["roofline_spmm"] = o2["roofline_spmm"]
-            if not args.no_cpu_baseline:
-                extra["cpu_baseline"], _ = cpu_baseline(wl2, ld2, steps=1, warmup=1)
-            out["workloads"] = {WORKLOAD_NAMES["baby"]: extra}
+            out["workloads"] = {}
+            for name in EXTRA_WORKLOADS:
+                o2, c2 = run_gpu(args, name, 20, 5, main=False)
+                extra = {kk: o2[kk] for kk in ("value", "unit", "ms_per_step", "propagation_step_ms", "spmm_hbm_GBs", "e2e",
+                                               "gpu_launches", "metrics", "config", "roofline_spmm", "kernels")}
+                if not args.no_cpu_baseline:
+                    extra["cpu_baseline"], _, ref2 = cpu_baseline(c2["wl"], c2["loader"], steps=1, warmup=1,
+                                                                  model_name=c2["model_name"])
+                    extra["parity"] = parity_vs_cpu(c2, ref2)
+                    if not extra["parity"]["ok"] and failed is None:
+                        failed = "workload %s: GPU arm differs from the CPU restatement: %r" % (name, extra["parity"])
+                    del ref2
+                out["workloads"][WORKLOADS[name][2]] = extra
+                del o2, c2
+                torch.cuda.empty_cache()
         out_stream.write(json.dumps(out) + "\n")
         out_stream.flush()
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
         dist.destroy_process_group()
+    if failed is not None:
+        sys.stderr.write("[bench] PARITY FAILURE: %s\n" % failed)
+        sys.exit(3)
 
 
 if __name__ == "__main__":

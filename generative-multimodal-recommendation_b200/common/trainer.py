@@ -75,6 +75,7 @@ class Trainer(object):
             return out
 
         replay.graph = graph
+        ops.note_graph_captured()   # workspaces this graph points into must outlive it (ops._ws)
         return replay
 
     def fit(self, *args, **kwargs):

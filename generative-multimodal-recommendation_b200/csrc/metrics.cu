@@ -47,10 +47,11 @@ __global__ void __launch_bounds__(kMU)
     const double n = (double)(hi - lo);
     const int lim = (int)min((int64_t)K, hi - lo);
     double c = 0.0, dcg = 0.0, idcg = 0.0, sp = 0.0;
-    // c / n, dcg / idcg, sp / min(pos + 1, lim) as of the last change (0 / 0 = NaN for a user without ground truth, as
-    // the literal expressions give)
-    const double q0 = (hi > lo) ? 0.0 : nan("");
-    double q_recall = q0, q_ndcg = q0, q_map = q0;
+    // c / n, dcg / idcg, sp / min(pos + 1, lim) as of the last change.  A user WITHOUT ground truth (the reference's
+    // loaders never produce one) gets what GenMMRec/src/utils/metrics.py computes for pos_len == 0: recall = 0 / 0 = NaN,
+    // but NDCG and MAP = 0, because `idcg[row, 0:] = idcg[row, -1]` (:54-55) and `ranges[0:] = ranges[-1]` (:86-87) wrap
+    // around to the full-length normalisers.
+    double q_recall = (hi > lo) ? 0.0 : nan(""), q_ndcg = 0.0, q_map = 0.0;
 
     for (int k0 = 0; k0 < K; k0 += kKC) {
         const int kc = min(kKC, K - k0);

@@ -534,8 +534,8 @@ static int spmm_common(const gmr_spmm_plan* plan, const int32_t* rowptr, const i
 // ---- row-wise glue ---------------------------------------------------------------------------
 // out = a*x + b*y + c * z / max(||z||_2, eps); one warp per row.
 __global__ void __launch_bounds__(256)
-    rows_axpby_norm_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ y, int64_t ldy,
-                           const float* __restrict__ z, int64_t ldz, float* __restrict__ out, int64_t ldo,
+    rows_axpby_norm_kernel(const float* x, int64_t ldx, const float* y, int64_t ldy,   // no __restrict__: out may alias
+                           const float* z, int64_t ldz, float* out, int64_t ldo,       // x, y or z (in-place accumulate)
                            int64_t n_rows, int32_t D, float a, float b, float c, float eps)
 {
     const int lane = threadIdx.x & 31;
@@ -563,8 +563,8 @@ __global__ void __launch_bounds__(256)
 // D = 64, 16-byte aligned rows: 16 lanes x float4 per row, two rows per warp, one 128-bit load per operand and lane
 // (the generic kernel's 4-byte loads reach a third of the copy bandwidth on this 1.2 GB pass).
 __global__ void __launch_bounds__(256)
-    rows_axpby_norm_d64_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ y, int64_t ldy,
-                               const float* __restrict__ z, int64_t ldz, float* __restrict__ out, int64_t ldo,
+    rows_axpby_norm_d64_kernel(const float* x, int64_t ldx, const float* y, int64_t ldy,   // no __restrict__: out may alias
+                               const float* z, int64_t ldz, float* out, int64_t ldo,       // x, y or z
                                int64_t n_rows, float a, float b, float c, float eps)
 {
     const int lane = threadIdx.x & 31, sub = lane & 15;

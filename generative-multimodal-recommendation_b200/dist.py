@@ -1,16 +1,18 @@
 """One-process-per-GPU sharding of the hot path.
 
 Propagation is row-sharded: rank g owns a contiguous block of user rows and a contiguous block of item
-rows of every graph.  A layer output that the NEXT SpMM needs in full is produced by the fused kernel
-``gmr_spmm_csr_f32_push``: each rank computes its rows and stores them straight into every peer's copy
-of the gathered operand through NVLink peer memory (CUDA IPC mappings) -- the all-gather rides inside
-the SpMM epilogue, tile by tile, instead of following it as a separate NCCL collective.  A tiny
-stream-ordered NCCL all-reduce then acts as the cross-rank barrier.  Evaluation is sharded by the same
-user blocks; every rank scores its users against the full item table and only the [4, K] float64
-metric sums are all-reduced.
+rows of every graph.  A layer output that the NEXT SpMM needs in full lives in a buffer replicated on
+every rank (CUDA IPC peer mappings); each rank computes its row block with the local SpMM kernel (K1) and
+then stores the block into every peer's replica over NVLink with ``gmr_rows_push_f32`` (a copy kernel on a
+second stream, overlapped with the SpMMs that do not depend on it).  A tiny stream-ordered NCCL all-reduce
+then acts as the cross-rank barrier.  The fused variant ``gmr_spmm_csr_f32_push`` (stores from the SpMM
+epilogue) exists and is tested, but is NOT on this path: remote stores stall the gather warps and it
+measured slower than SpMM + copy kernel.  Evaluation is sharded by the same user
+blocks; every rank scores its users against the full item table and only the [4, K] float64 metric sums
+are all-reduced.
 
-``torch.distributed`` is plumbing here (rendezvous, handle exchange, barrier, the small dense
-all-gathers around the torch projections); the data path of the gathered SpMM operand is our kernel.
+``torch.distributed`` is plumbing here (rendezvous, handle exchange, barriers); the data path of the
+gathered SpMM operand is our kernels over peer memory.
 """
 import ctypes as C
 import os
@@ -111,7 +113,7 @@ def spmm_push(a, x, ptr_table, n_peers, row_offset, ldy, alpha=1.0):
     xp, ldx = ops._rows(x, "X")
     plan = a.plan
     need = lib.gmr_spmm_workspace_bytes(plan, d)
-    ws = ops._ws(x.device, need, "spmm") if need > 0 else None
+    ws = ops._ws(x.device, need, "spmm_push") if need > 0 else None   # own buffer: may run beside spmm_raw on another stream
     with torch.cuda.device(x.device):
         ev = ops._prof_begin()
         _lib.check(lib.gmr_spmm_csr_f32_push(plan, ops._ptr(a.rowptr), ops._ptr(a.col), ops._ptr(a.val), xp, ldx,

@@ -99,7 +99,7 @@ class DiffMM(GeneralRecommender):
         self.image_UI_matrix = self.edgeDropper(self.build_ui_matrix(*image_edges), self.device)
         self.text_UI_matrix = self.edgeDropper(self.build_ui_matrix(*text_edges), self.device)
 
-    # ---- feature projections (dense, torch/cuBLAS: SURVEY.md a8) ------------------------------------
+    # ---- feature projections: `_project` below takes the tcgen05 kernel; these two keep autograd --------
     def getItemEmbeds(self):
         return self.iEmbeds
 
@@ -202,7 +202,7 @@ class DiffMM(GeneralRecommender):
         # work[:, d:] is `modal` (row pitch 2d); work[:nu, :d] receives R_hat Z
         work = torch.empty((n, 2 * d), dtype=torch.float32, device=self.device)
         spmm_raw(adj.ui, xi, out=work[:nu])                           # users: [R_hat Z | modal_u]
-        xu = torch.add(u0, work[:nu, :d])                             # U0 + R_hat Z
+        xu = rows_axpby_norm(u0, work[:nu, :d], None, a=1.0, b=1.0)   # U0 + R_hat Z
         modal = work[:, d:]
         spmm_raw(adj.iu, xu, out=modal[nu:])                          # items: modal_i
         spmm_raw(self._modal_mix_graph(image_adj, text_adj, w0, w1), e0, out=modal, beta=1.0)   # += lambda (w0 A_v + w1 A_t) E0

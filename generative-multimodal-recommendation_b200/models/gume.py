@@ -16,7 +16,7 @@ import torch.nn.functional as F
 
 from ..common.abstract_recommender import GeneralRecommender
 from .. import graph as gb
-from ..ops import GraphCSR, spmm, spmm_raw
+from ..ops import GraphCSR, linear_proj, spmm, spmm_raw
 
 
 class GUME(GeneralRecommender):
@@ -29,6 +29,10 @@ class GUME(GeneralRecommender):
         self.knn_k = config["knn_k"]
         self.n_layers = config["n_layers"]
         self.knn_builder = config["knn_builder"] or "fused"  # fused (K2, no I x I matrix) | dense
+        # weights / temperatures of the auxiliary training terms (gume.py:33-41 of the reference)
+        self.reg_weight_2 = config["reg_weight_2"]
+        self.bm_loss, self.um_loss, self.vt_loss = config["bm_loss"], config["um_loss"], config["vt_loss"]
+        self.bm_temp, self.um_temp = config["bm_temp"], config["um_temp"]
 
         self.interaction_matrix = dataset.inter_matrix(form="coo")
         d = self.embedding_dim
@@ -87,8 +91,11 @@ class GUME(GeneralRecommender):
     def forward(self, adj, train=False):
         item_embeds = self.item_id_embedding.weight
         user_embeds = self.user_embedding.weight
-        image_item_embeds = torch.multiply(item_embeds, self.image_space_trans(self.image_embedding.weight))
-        text_item_embeds = torch.multiply(item_embeds, self.text_space_trans(self.text_embedding.weight))
+        # [I, 4096] / [I, 384] feature tables x Linear(., 64): the tcgen05 projection kernel under no_grad
+        image_item_embeds = torch.multiply(item_embeds, self.image_trans_dim(
+            linear_proj(self.image_embedding.weight, self.image_reduce_dim)))
+        text_item_embeds = torch.multiply(item_embeds, self.text_trans_dim(
+            linear_proj(self.text_embedding.weight, self.text_reduce_dim)))
 
         explicit_image_item = self.conv_ii(self.image_original_adj, image_item_embeds)
         explicit_text_item = self.conv_ii(self.text_original_adj, text_item_embeds)
@@ -126,13 +133,48 @@ class GUME(GeneralRecommender):
         e = self.forward(self.norm_adj)
         return e[:self.n_users], e[self.n_users:]
 
+    # ---- training objective (GenMMRec/src/models/gume.py:278-412), differentiable through ops.spmm ------------------
+    @staticmethod
+    def InfoNCE(view1, view2, temperature, chunk_size=4096):
+        """-log( exp(<a_i, b_i> / T) / sum_j exp(<a_i, b_j> / T) + 1e-8 ), mean over i, rows L2-normalised; the
+        denominator is accumulated over column chunks so that the [N, N] similarity matrix is never held whole."""
+        a, b = F.normalize(view1, dim=1), F.normalize(view2, dim=1)
+        pos = torch.exp((a * b).sum(dim=-1) / temperature)
+        total = torch.zeros_like(pos)
+        for j in range(0, b.shape[0], chunk_size):
+            total = total + torch.exp(a @ b[j:j + chunk_size].t() / temperature).sum(dim=1)
+        return (-torch.log(pos / total + 1e-8)).mean()
+
+    def cal_noise_loss(self, idx, emb, temp):
+        """InfoNCE between two randomly perturbed views of `emb` (sign-preserving noise of norm 0.1), rows `idx`."""
+        def perturbed(x):
+            return x + torch.sign(x) * F.normalize(torch.rand_like(x), dim=-1) * 0.1
+
+        return self.InfoNCE(perturbed(emb)[idx], perturbed(emb)[idx], temp)
+
+    @staticmethod
+    def align_vt(e1, e2):
+        """|var - var| + |mean - mean| of the two explicit modality embeddings."""
+        return (torch.abs(torch.var(e1) - torch.var(e2)) + torch.abs(torch.mean(e1) - torch.mean(e2))).mean()
+
     def calculate_loss(self, interaction):
-        """BPR term of gume.py (the InfoNCE / alignment auxiliaries are training-only extras outside
-        the hot path)."""
+        """BPR + L2 + behaviour/modality alignment (InfoNCE) + visual/text alignment + user-modality enhancement: the
+        full objective of gume.py:357-395."""
         users, pos_items, neg_items = interaction[0], interaction[1], interaction[2]
-        e, _, _ = self.forward(self.norm_adj, train=True)
-        ue, ie = e[:self.n_users], e[self.n_users:]
+        nu, ni = self.n_users, self.n_items
+        e, (integration, ext_id, ext_it), (exp_img, exp_txt) = self.forward(self.norm_adj, train=True)
+        ue, ie = e[:nu], e[nu:]
         u, p, n = ue[users], ie[pos_items], ie[neg_items]
-        maxi = F.logsigmoid(torch.sum(u * p, dim=1) - torch.sum(u * n, dim=1))
-        reg = 0.5 * ((u ** 2).sum() + (p ** 2).sum() + (n ** 2).sum()) / self.batch_size
-        return -torch.mean(maxi) + self.reg_weight_1 * reg
+        bpr = -torch.mean(F.logsigmoid(torch.sum(u * p, dim=1) - torch.sum(u * n, dim=1)))
+        reg1 = self.reg_weight_1 * 0.5 * ((u ** 2).sum() + (p ** 2).sum() + (n ** 2).sum()) / self.batch_size
+        int_u, int_i = integration[:nu], integration[nu:]
+        id_u, id_i = ext_id[:nu], ext_id[nu:]
+        it_u, it_i = ext_it[:nu], ext_it[nu:]
+        vt = self.vt_loss * self.align_vt(exp_img, exp_txt)
+        bm = self.bm_loss * (self.InfoNCE(int_u[users], id_u[users], self.bm_temp)
+                             + self.InfoNCE(int_i[pos_items], id_i[pos_items], self.bm_temp))
+        um = self.um_loss * (self.InfoNCE(it_u[users], int_u[users], self.um_temp)
+                             + self.cal_noise_loss(users, int_u, self.um_temp)
+                             + self.cal_noise_loss(users, it_u, self.um_temp))
+        reg2 = self.reg_weight_2 * 0.5 * (it_i[pos_items] ** 2).sum() / self.batch_size
+        return bpr + (vt + bm) + um + (reg1 + reg2)

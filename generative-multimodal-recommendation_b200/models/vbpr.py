@@ -6,6 +6,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..common.abstract_recommender import GeneralRecommender
+from ..ops import linear_proj
 from ._common import bpr_loss, emb_loss
 
 
@@ -27,7 +28,8 @@ class VBPR(GeneralRecommender):
         nn.init.constant_(self.item_linear.bias, 0)
 
     def forward(self, dropout=0.0):
-        item_embeddings = torch.cat((self.i_embedding, self.item_linear(self.item_raw_features)), -1)
+        # [I, 4480] x Linear(4480, 64): the tcgen05 projection kernel under no_grad (ops.linear_proj)
+        item_embeddings = torch.cat((self.i_embedding, linear_proj(self.item_raw_features, self.item_linear)), -1)
         return F.dropout(self.u_embedding, dropout), F.dropout(item_embeddings, dropout)
 
     def propagate(self):

@@ -21,6 +21,17 @@ LAUNCHES = 0
 PROFILE = None
 
 _workspaces = {}
+# Superseded workspaces are kept alive once a CUDA graph has captured the step (Trainer.graphed): a captured kernel has the
+# old buffer's address baked in, and handing that memory back to the allocator would let a later replay write into someone
+# else's tensor.  Grow-only buffers and a handful of growth events bound what this holds.
+_retired = []
+_graphs_captured = 0
+
+
+def note_graph_captured():
+    """Called by Trainer.graphed after a capture: from now on replaced workspaces are retired, not freed."""
+    global _graphs_captured
+    _graphs_captured += 1
 
 
 def _prof_begin():
@@ -43,6 +54,8 @@ def _ws(device, nbytes, tag="default"):
     key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
+        if buf is not None and _graphs_captured > 0:
+            _retired.append(buf)
         buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
         _workspaces[key] = buf
     return buf
@@ -371,6 +384,22 @@ def dense_proj(a, w, out=None):
                    "gmr_dense_proj_f32")
     LAUNCHES += 2
     return out
+
+
+def linear_proj(x, linear):
+    """``linear(x)`` for an ``nn.Linear`` with 64 outputs over a wide feature table (GUME's image/text_reduce_dim,
+    gume.py:232-233; VBPR's item_linear, vbpr.py:69-75): the split-TF32 tcgen05 kernel under ``no_grad`` when the shape
+    fits it, the library GEMM otherwise (training needs autograd; other shapes are not implemented)."""
+    w = linear.weight
+    if (not torch.is_grad_enabled()) and x.is_cuda and x.dim() == 2 and w.shape[0] == 64 and w.shape[1] % 32 == 0:
+        wt = w.detach().t().contiguous()           # [K, 64]
+        xc = x.detach()
+        if dense_proj_supported(xc, wt):
+            out = dense_proj(xc, wt)
+            if linear.bias is not None:
+                out += linear.bias.detach()
+            return out
+    return linear(x)
 
 
 def tc_supported(d, k, precision="tc"):

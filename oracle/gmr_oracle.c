@@ -174,8 +174,10 @@ void oracle_metrics(const uint8_t* hit, const int64_t* gt_len, int32_t U, int32_
             sp += h * (c / (double)(k + 1));
             recall[k] += c / n;
             precision[k] += c / (double)(k + 1);
-            ndcg[k] += dcg / idcg;
-            map[k] += sp / (double)((k + 1) < lim ? (k + 1) : lim);
+            /* gt_len == 0 (never produced by the reference's loaders): metrics.py:54-55,86-87 index with -1 and wrap to
+             * the full-length normalisers, so NDCG and MAP are 0 there while recall is 0 / 0 = NaN */
+            ndcg[k] += (lim > 0) ? dcg / idcg : 0.0;
+            map[k] += (lim > 0) ? sp / (double)((k + 1) < lim ? (k + 1) : lim) : 0.0;
         }
     }
     for (int32_t k = 0; k < K; ++k) {

@@ -3,6 +3,8 @@
 
     python tests/golden/make_golden.py            # toy fixtures for all six models + op fixtures
     python tests/golden/make_golden.py --baby     # additionally the Baby-shape samples
+    python tests/golden/make_golden.py --skip-toy --sports     # GenRecV1 at the Sports shape (BASELINE config 3)
+    python tests/golden/make_golden.py --skip-toy --clothing   # LD4MRec at the Clothing shape (BASELINE config 4)
     python tests/golden/make_golden.py --evaluator-only   # just the is_test evaluator dicts
 
 The reference holds no golden vectors of its own (five smoke scripts asserting a
@@ -142,8 +144,13 @@ def run_model(name, data_root, dataset, shape, out_path, sample=None, store_para
                 out["param/" + k] = v.cpu().numpy()
     if name == "LD4MRec":
         out["buf/user_svd_emb"] = model.user_svd_emb.cpu().numpy()
-        out["buf/user_mm_emb"] = model.user_mm_emb.cpu().numpy() if sample is None else \
-            model.user_mm_emb.cpu().numpy()[sample["users"]]
+        mm = model.user_mm_emb.cpu().numpy()
+        if sample is None:
+            out["buf/user_mm_emb"] = mm
+        else:  # 32 sampled rows of the [n_users, 4480] wide-SpMM output + its scale
+            out["buf/user_mm_emb/rows"] = sample["users"][:32].astype(np.int64)
+            out["buf/user_mm_emb/values"] = mm[sample["users"][:32]]
+            out["buf/user_mm_emb/maxabs"] = np.asarray([np.abs(mm[sample["users"]]).max()], dtype=np.float64)
     rng = np.random.default_rng(5)
     for attr, (idx, val) in graphs.items():
         if sample is None:
@@ -311,6 +318,8 @@ def evaluator_fixtures(out_path):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--baby", action="store_true")
+    ap.add_argument("--sports", action="store_true", help="GenRecV1 at the Sports shape (sampled fixture)")
+    ap.add_argument("--clothing", action="store_true", help="LD4MRec at the Clothing shape (sampled fixture)")
     ap.add_argument("--models", default="DiffMM,GUME,GenRecV1,LD4MRec,VBPR,LightGCN")
     ap.add_argument("--skip-toy", action="store_true")
     ap.add_argument("--evaluator-only", action="store_true", help="only (re)write evaluator_extras.npz")
@@ -353,6 +362,21 @@ def main():
                     os.symlink(os.path.join(tmp, "baby", f), os.path.join(d, "baby", f))
                 run_model(name, d, "baby", (nu, ni), os.path.join(HERE, "baby_%s.npz" % name.lower()),
                           sample=sample, store_params=False)
+        # BASELINE configs 3 and 4: one model each at its own shape, sampled like the Baby fixtures
+        for flag, shape_name, name in ((args.sports, "sports", "GenRecV1"), (args.clothing, "clothing", "LD4MRec")):
+            if not flag:
+                continue
+            nu, ni, nn, split = synth.SHAPES[shape_name]
+            synth.write_dataset(tmp, shape_name, nu, ni, nn, split=split)
+            rng = np.random.default_rng(78)
+            sample = {
+                "users": np.sort(rng.choice(nu, 256, replace=False)),
+                "items": np.sort(rng.choice(ni, 256, replace=False)),
+                "eval_pos": np.sort(np.concatenate([np.arange(128), rng.choice(np.arange(128, int(nu * 0.95)), 384,
+                                                                                 replace=False)])),
+            }
+            run_model(name, tmp, shape_name, (nu, ni), os.path.join(HERE, "%s_%s.npz" % (shape_name, name.lower())),
+                      sample=sample, store_params=False)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 

@@ -522,3 +522,25 @@ def test_dense_proj_unsupported_is_loud(ops):
     assert not ops.dense_proj_supported(a, torch.zeros(48, 64, device="cuda"))
     with pytest.raises(RuntimeError):
         ops.dense_proj(a, torch.zeros(48, 64, device="cuda"))
+
+
+def test_metrics_kernel_for_a_user_without_ground_truth(ops):
+    """Same answer as the reference's metric code (and the oracle) for pos_len == 0: NaN recall, zero NDCG / MAP
+    (tests/test_oracle_properties.py::test_metrics_for_a_user_without_ground_truth pins the oracle to the reference)."""
+    rng = np.random.default_rng(5)
+    u, k, n_items = 200, 20, 90
+    topk = np.stack([rng.choice(n_items, size=k, replace=False) for _ in range(u)]).astype(np.int32)
+    lens = rng.integers(1, 9, size=u)
+    lens[[3, 77, 199]] = 0
+    gts = [np.sort(rng.choice(n_items, size=int(n), replace=False)) for n in lens]
+    rowptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    items = np.concatenate(gts).astype(np.int32)
+    sums, hit = ops.hits_metrics(torch.from_numpy(topk).cuda(), torch.from_numpy(rowptr).cuda(), torch.from_numpy(items).cuda(),
+                                 return_hit=True)
+    got = (sums / u).cpu().numpy()
+    ref_hit = c_api.hits(topk, rowptr, items)
+    assert np.array_equal(hit.cpu().numpy(), ref_hit)
+    ref = c_api.metrics(ref_hit, lens.astype(np.int64))
+    assert np.all(np.isnan(got[0])) and np.all(np.isnan(ref["recall"]))
+    for j, name in ((1, "ndcg"), (2, "precision"), (3, "map")):
+        assert np.all(np.isfinite(got[j])) and np.abs(got[j] - ref[name]).max() < 1e-12, name

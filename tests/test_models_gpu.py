@@ -235,6 +235,50 @@ def test_baby_shape_matches_reference(env, name):
     check_eval(env, cfg, model, loaders, z, sampled=True)
 
 
+@pytest.mark.parametrize("shape_name,name", [("sports", "GenRecV1"), ("clothing", "LD4MRec")])
+def test_sports_clothing_shapes_match_reference(env, shape_name, name):
+    """BASELINE configs 3 and 4 at their own shapes: GenRecV1 on Sports (the content embedding full_sort_predict
+    contracts: user_item_GCN x 2) and LD4MRec on Clothing (wide D = 4480 SpMM, sparse item_proj, [B, hidden] x
+    [hidden, n_items] + bias scoring), against vectors the unmodified reference produced
+    (tests/golden/make_golden.py --sports --clothing)."""
+    z, meta = load_golden("%s_%s" % (shape_name, name.lower()))
+    nu, ni, nn, split = env.synth.SHAPES[shape_name]
+    users, items, label = env.synth.make_interactions(nu, ni, nn, split=split)
+    img, txt = env.synth.make_features(ni)
+    data = dict(users=users, items=items, label=label, img=img, txt=txt, n_users=nu, n_items=ni)
+    cfg, model, loaders = build(env, name, meta, data, shape_name)
+    shapes = {k: tuple(s) for k, s in meta["param_names"]}
+    params = env.synth.make_params(shapes)
+    sd = model.state_dict()
+    with torch.no_grad():
+        for k, v in params.items():
+            if k in sd:
+                sd[k].copy_(torch.from_numpy(v).to(sd[k].device))
+    model.invalidate_cache()
+    if name == "GenRecV1":
+        u, i = env.synth.generated_edges(nu, ni, meta["config"]["rebuild_k"], seed=11)
+        torch.manual_seed(11)
+        model.set_generated_edges((u, i))   # the kNN item-item graphs only feed the side embedding evaluation discards
+        with torch.no_grad():
+            ue, ie = model.propagate()
+        for lab, e in (("user", ue.detach()), ("item", ie.detach())):
+            rows = z["emb/%s/rows" % lab]
+            got = e[torch.from_numpy(rows).to(e.device)].cpu().numpy()
+            assert np.abs(got.astype(np.float64) - z["emb/%s/values" % lab]).max() / z["emb/%s/maxabs" % lab][0] < EMB_TOL
+            assert abs(float(e.double().sum()) - z["emb/%s/sum" % lab][0]) <= 1e-5 * float(e.double().abs().sum())
+    else:
+        model.user_svd_emb = torch.from_numpy(z["buf/user_svd_emb"]).to(model.device)
+        rows = torch.from_numpy(z["buf/user_mm_emb/rows"]).to(model.device)
+        got = model.user_mm_emb[rows].cpu().numpy().astype(np.float64)   # the D = 4480 SpMM of ld4mrec.py:206
+        assert np.abs(got - z["buf/user_mm_emb/values"]).max() / z["buf/user_mm_emb/maxabs"][0] < EMB_TOL
+    with torch.no_grad():
+        first = next(iter(loaders["valid"]))
+        loaders["valid"].pr = 0
+        s0 = model.full_sort_predict(first)
+        assert rel_err(s0[:8].cpu().numpy(), z["scores0/values"]) < 2e-5
+    check_eval(env, cfg, model, loaders, z, sampled=True)
+
+
 def test_knn_builders_gpu(env):
     """kNN graph through the fused score+top-K kernel (no I x I matrix) vs the dense reference-shaped
     builder: same neighbours except where the similarity gap is below the tie tolerance, weights

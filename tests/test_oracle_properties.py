@@ -84,6 +84,47 @@ def test_hits_and_metrics_oracles_vs_reference_expressions(seed, u, k, n_items, 
     assert np.all((c["ndcg"] >= 0) & (c["ndcg"] <= 1 + 1e-12))
 
 
+def _reference_metric_loops(pos_index, pos_len):
+    """ndcg_ / map_ / recall_ exactly as GenMMRec/src/utils/metrics.py:12-15,47-63,78-89 write them, including the per-row
+    Python loops whose `idx - 1` / `lens - 1` index wraps around for a user without ground truth."""
+    k = pos_index.shape[1]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        recall = (np.cumsum(pos_index, axis=1) / pos_len.reshape(-1, 1)).mean(axis=0)
+    idcg_len = np.where(pos_len > k, k, pos_len)
+    iranks = np.zeros_like(pos_index, dtype=float)
+    iranks[:, :] = np.arange(1, k + 1)
+    idcg = np.cumsum(1.0 / np.log2(iranks + 1), axis=1)
+    for row, idx in enumerate(idcg_len):
+        idcg[row, idx:] = idcg[row, idx - 1]
+    dcg = np.cumsum(np.where(pos_index, 1.0 / np.log2(iranks + 1), 0), axis=1)
+    ndcg = (dcg / idcg).mean(axis=0)
+    pre = pos_index.cumsum(axis=1) / np.arange(1, k + 1)
+    sum_pre = np.cumsum(pre * pos_index.astype(float), axis=1)
+    result = np.zeros_like(pos_index, dtype=float)
+    for row, lens in enumerate(idcg_len):
+        ranges = np.arange(1, k + 1)
+        ranges[lens:] = ranges[lens - 1]
+        result[row] = sum_pre[row] / ranges
+    return {"recall": recall, "ndcg": ndcg, "map": result.mean(axis=0)}
+
+
+def test_metrics_for_a_user_without_ground_truth():
+    """pos_len == 0 never comes out of the reference's loaders, but its metric code has a defined answer for it: recall is
+    0 / 0 = NaN while NDCG and MAP are 0 (the -1 indices wrap to the full-length normalisers).  Both oracles say the same."""
+    rng = np.random.default_rng(3)
+    hit = rng.random((6, 20)) < 0.2
+    pos_len = np.array([3, 0, 25, 1, 0, 7], dtype=np.int64)
+    hit[pos_len == 0] = False
+    want = _reference_metric_loops(hit, pos_len)
+    c = c_api.metrics(hit, pos_len)
+    for name in ("ndcg", "map"):
+        assert np.all(np.isfinite(want[name]))
+        assert np.abs(c[name] - want[name]).max() < 1e-12, name
+        with np.errstate(divide="ignore", invalid="ignore"):
+            assert np.abs(rp.METRICS[name](hit, pos_len) - want[name]).max() < 1e-12, name
+    assert np.all(np.isnan(want["recall"])) and np.all(np.isnan(c["recall"]))
+
+
 @settings(**SETTINGS)
 @given(seed=st.integers(0, 2**31 - 1), n_rows=st.integers(1, 40), n_cols=st.integers(1, 40), d=st.sampled_from([1, 5, 64]),
        nnz=st.integers(0, 300))
