@@ -605,7 +605,7 @@ class CpuReference(object):
         elif model_name == "GenRecV1":
             self.adj, self.img_adj = coo(m.norm_adj.full), coo(m.image_UI_matrix)
         elif model_name == "LD4MRec":
-            self.r = coo(m.R)
+            self.r_rowptr, self.r_col, self.r_val = m.R.rowptr.cpu().long(), m.R.col.cpu().long(), m.R.val.cpu()
             self.user_svd, self.user_mm = m.user_svd_emb.cpu(), m.user_mm_emb.cpu()
         if m.v_feat is not None:
             self.v_feat, self.t_feat = m.v_feat.cpu(), m.t_feat.cpu()
@@ -631,10 +631,14 @@ class CpuReference(object):
         elif self.name == "VBPR":
             ue, ie = rp.vbpr_forward(p, self.t_feat, self.v_feat)
         elif self.name == "GenRecV1":
-            c = rp.genrecv1_content(p, self.adj, self.img_adj, self.nu, cfg["n_layers"])
-            ue, ie = c[:self.nu], c[self.nu:]
+            ue, ie = rp.genrecv1_content(p, self.adj, self.img_adj, self.nu, cfg["n_layers"])
         elif self.name == "LD4MRec":
-            x_in = torch.index_select(self.r, 0, self.users).to_dense()   # [B, n_items] history rows (ld4mrec.py:357-359)
+            # [B, n_items] dense history rows, what the reference slices out of its scipy CSR (ld4mrec.py:357-359)
+            lo, hi = self.r_rowptr[self.users], self.r_rowptr[self.users + 1]
+            rows = torch.repeat_interleave(torch.arange(self.users.numel()), hi - lo)
+            src = torch.repeat_interleave(lo - torch.cumsum(hi - lo, 0) + (hi - lo), hi - lo) + torch.arange(rows.numel())
+            x_in = torch.zeros((self.users.numel(), self.ni))
+            x_in.index_put_((rows, self.r_col[src]), self.r_val[src], accumulate=True)
             h = rp.ld4mrec_hidden(p, x_in, self.user_svd[self.users], self.user_mm[self.users], cfg["cnet_n_layers"])
             t1 = time.perf_counter()
             return None, None, torch.addmm(p["cnet.output_proj.bias"], h, p["cnet.output_proj.weight"].t()), t1
@@ -857,18 +861,22 @@ def main():
             torch.cuda.empty_cache()
             out["workloads"] = {}
             for name in EXTRA_WORKLOADS:
-                o2, c2 = run_gpu(args, name, 20, 5, main=False)
-                extra = {kk: o2[kk] for kk in ("value", "unit", "ms_per_step", "propagation_step_ms", "spmm_hbm_GBs", "e2e",
-                                               "gpu_launches", "metrics", "config", "roofline_spmm", "kernels")}
-                if not args.no_cpu_baseline:
-                    extra["cpu_baseline"], _, ref2 = cpu_baseline(c2["wl"], c2["loader"], steps=1, warmup=1,
-                                                                  model_name=c2["model_name"])
-                    extra["parity"] = parity_vs_cpu(c2, ref2)
-                    if not extra["parity"]["ok"] and failed is None:
-                        failed = "workload %s: GPU arm differs from the CPU restatement: %r" % (name, extra["parity"])
-                    del ref2
+                try:
+                    o2, c2 = run_gpu(args, name, 20, 5, main=False)
+                    extra = {kk: o2[kk] for kk in ("value", "unit", "ms_per_step", "propagation_step_ms", "spmm_hbm_GBs", "e2e",
+                                                   "gpu_launches", "metrics", "config", "roofline_spmm", "kernels")}
+                    if not args.no_cpu_baseline:
+                        extra["cpu_baseline"], _, ref2 = cpu_baseline(c2["wl"], c2["loader"], steps=1, warmup=1,
+                                                                      model_name=c2["model_name"])
+                        extra["parity"] = parity_vs_cpu(c2, ref2)
+                        if not extra["parity"]["ok"] and failed is None:
+                            failed = "workload %s: GPU arm differs from the CPU restatement: %r" % (name, extra["parity"])
+                        del ref2
+                    del o2, c2
+                except Exception as e:  # a side workload must not cost the headline line
+                    import traceback
+                    extra = {"error": repr(e), "traceback": traceback.format_exc()[-1500:]}
                 out["workloads"][WORKLOADS[name][2]] = extra
-                del o2, c2
                 torch.cuda.empty_cache()
         out_stream.write(json.dumps(out) + "\n")
         out_stream.flush()
