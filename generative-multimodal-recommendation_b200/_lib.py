@@ -51,6 +51,9 @@ SIGNATURES = {
                                              _f32, _vp]),
     "gmr_dense_proj_workspace_bytes": (_i64, [_i32, _i32]),
     "gmr_dense_proj_f32": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _i64, _i32, _vp, _i64, _vp, _i64, _vp]),
+    "gmr_bpr_scores_f32": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "gmr_bpr_scores_backward_f32": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _i64,
+                                              _vp]),
     "gmr_peer_alloc": (C.c_int, [C.POINTER(_vp), _i64]),
     "gmr_peer_free": (C.c_int, [_vp]),
     "gmr_peer_export": (C.c_int, [_vp, C.c_char_p]),

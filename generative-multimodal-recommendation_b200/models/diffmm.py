@@ -240,19 +240,28 @@ class DiffMM(GeneralRecommender):
         return embeds[:nu], embeds[nu:]
 
     def forward_cl_MM(self, adj, image_adj, text_adj):
+        """The two contrastive views (diffmm.py:171-195).  Each view starts on its own modality graph; the
+        ``gnn_layer`` propagation steps over the shared adjacency then run as ONE chain over a 2d-wide right-hand side
+        (both views side by side): half the passes over ``adj``, differentiable through ``ops.spmm``."""
         adj, image_adj, text_adj = as_graph(adj), as_graph(image_adj), as_graph(text_adj)
-        nu = self.n_users
-
-        def view(m_adj, feats):
-            e = spmm(m_adj, torch.concat([self.uEmbeds, F.normalize(feats)]))
-            lst = [e]
-            for _ in range(self.gnn_layer):
-                lst.append(spmm(adj, lst[-1]))
-            return sum(lst)
-
-        e1 = view(image_adj, self.getImageFeats())
-        e2 = view(text_adj, self.getTextFeats())
+        nu, d = self.n_users, self.latdim
+        e1 = spmm(image_adj, torch.concat([self.uEmbeds, F.normalize(self.getImageFeats())]))
+        e2 = spmm(text_adj, torch.concat([self.uEmbeds, F.normalize(self.getTextFeats())]))
+        last = torch.cat([e1, e2], dim=1)
+        total = last
+        for _ in range(self.gnn_layer):
+            last = spmm(adj, last)
+            total = total + last
+        e1, e2 = total[:, :d], total[:, d:]
         return e1[:nu], e1[nu:], e2[:nu], e2[nu:]
+
+    @staticmethod
+    def edges_from_denoised(batch_index, denoised_batch, k):
+        """(u, i) edge lists from one batch of denoised interaction rows: the ``rebuild_k`` best items of every user,
+        on the device -- what the reference's trainer extracts with a per-element ``.cpu().numpy()`` double loop
+        (GenMMRec/src/common/trainer.py:540-562).  Same edges in the same order."""
+        _, idx = torch.topk(denoised_batch, k=k)
+        return batch_index.to(torch.int64).repeat_interleave(k), idx.reshape(-1).to(torch.int64)
 
     def propagate(self):
         if self.image_UI_matrix is None or self.text_UI_matrix is None:
@@ -277,8 +286,8 @@ class DiffMM(GeneralRecommender):
         if self.image_UI_matrix is None or self.text_UI_matrix is None:
             return torch.tensor(0.0, requires_grad=True).to(self.device)
         usr, itm = self.forward_MM(self.norm_adj, self.image_UI_matrix, self.text_UI_matrix)
-        anc, pos, neg = usr[users], itm[pos_items], itm[neg_items]
-        bpr = -torch.log(1e-10 + torch.sigmoid((anc * pos).sum(dim=1) - (anc * neg).sum(dim=1))).mean()
+        ps, ns = ops.bpr_scores(usr, itm, users, pos_items, neg_items)   # fused gather + dot (csrc/train_ops.cu)
+        bpr = -torch.log(1e-10 + torch.sigmoid(ps - ns)).mean()
         reg = self.reg_loss() * self.reg_weight
         u1, i1, u2, i2 = self.forward_cl_MM(self.norm_adj, self.image_UI_matrix, self.text_UI_matrix)
         if self.cl_method == 1:

@@ -17,7 +17,7 @@ import torch.nn.functional as F
 
 from ..common.abstract_recommender import GeneralRecommender
 from .. import graph as gb
-from ..ops import GraphCSR, spmm
+from ..ops import GraphCSR, bpr_scores, spmm
 from ._common import BipartiteAdj, as_graph
 from .diffmm import SpAdjDropEdge
 
@@ -155,7 +155,7 @@ class GenRecV1(GeneralRecommender):
             return torch.tensor(0.0, requires_grad=True).to(self.device)
         c = self.content_embedding(self.norm_adj, self.image_UI_matrix)
         ue, ie = c[:self.n_users], c[self.n_users:]
-        u, p, n = ue[users], ie[pos_items], ie[neg_items]
-        bpr = -torch.mean(F.logsigmoid(torch.sum(u * p, dim=-1) - torch.sum(u * n, dim=-1)))
+        ps, ns = bpr_scores(ue, ie, users, pos_items, neg_items)   # fused gather + dot (csrc/train_ops.cu)
+        bpr = -torch.mean(F.logsigmoid(ps - ns))
         reg = self.user_embedding.weight.norm(2).square() + self.item_id_embedding.weight.norm(2).square()
         return bpr + reg * self.reg_weight

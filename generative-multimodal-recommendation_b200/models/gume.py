@@ -16,7 +16,7 @@ import torch.nn.functional as F
 
 from ..common.abstract_recommender import GeneralRecommender
 from .. import graph as gb
-from ..ops import GraphCSR, linear_proj, spmm, spmm_raw
+from ..ops import GraphCSR, bpr_scores, linear_proj, spmm, spmm_raw
 
 
 class GUME(GeneralRecommender):
@@ -165,7 +165,8 @@ class GUME(GeneralRecommender):
         e, (integration, ext_id, ext_it), (exp_img, exp_txt) = self.forward(self.norm_adj, train=True)
         ue, ie = e[:nu], e[nu:]
         u, p, n = ue[users], ie[pos_items], ie[neg_items]
-        bpr = -torch.mean(F.logsigmoid(torch.sum(u * p, dim=1) - torch.sum(u * n, dim=1)))
+        ps, ns = bpr_scores(ue, ie, users, pos_items, neg_items)   # fused gather + dot (csrc/train_ops.cu)
+        bpr = -torch.mean(F.logsigmoid(ps - ns))
         reg1 = self.reg_weight_1 * 0.5 * ((u ** 2).sum() + (p ** 2).sum() + (n ** 2).sum()) / self.batch_size
         int_u, int_i = integration[:nu], integration[nu:]
         id_u, id_i = ext_id[:nu], ext_id[nu:]

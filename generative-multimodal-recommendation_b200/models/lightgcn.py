@@ -10,6 +10,7 @@ import torch.nn as nn
 
 from ..common.abstract_recommender import GeneralRecommender
 from .. import graph as gb
+from ..ops import bpr_scores
 from ._common import BipartiteAdj, bpr_loss, emb_loss
 
 
@@ -52,8 +53,7 @@ class LightGCN(GeneralRecommender):
     def calculate_loss(self, interaction):
         user, pos_item, neg_item = interaction[0], interaction[1], interaction[2]
         ua, ia = self.forward()
-        u, p, n = ua[user, :], ia[pos_item, :], ia[neg_item, :]
-        mf = bpr_loss(torch.mul(u, p).sum(dim=1), torch.mul(u, n).sum(dim=1))
+        mf = bpr_loss(*bpr_scores(ua, ia, user, pos_item, neg_item))   # fused gather + dot (csrc/train_ops.cu)
         reg = emb_loss(self.embedding_dict["user_emb"][user, :], self.embedding_dict["item_emb"][pos_item, :],
                        self.embedding_dict["item_emb"][neg_item, :])
         return mf + self.reg_weight * reg

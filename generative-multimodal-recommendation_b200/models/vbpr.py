@@ -6,7 +6,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..common.abstract_recommender import GeneralRecommender
-from ..ops import linear_proj
+from ..ops import bpr_scores, linear_proj
 from ._common import bpr_loss, emb_loss
 
 
@@ -38,6 +38,5 @@ class VBPR(GeneralRecommender):
     def calculate_loss(self, interaction):
         user, pos_item, neg_item = interaction[0], interaction[1], interaction[2]
         ue, ie = self.forward()
-        u, p, n = ue[user, :], ie[pos_item, :], ie[neg_item, :]
-        mf = bpr_loss(torch.mul(u, p).sum(dim=1), torch.mul(u, n).sum(dim=1))
-        return mf + self.reg_weight * emb_loss(u, p, n)
+        mf = bpr_loss(*bpr_scores(ue, ie, user, pos_item, neg_item))   # fused gather + dot (csrc/train_ops.cu)
+        return mf + self.reg_weight * emb_loss(ue[user, :], ie[pos_item, :], ie[neg_item, :])

@@ -386,6 +386,56 @@ def dense_proj(a, w, out=None):
     return out
 
 
+class _BprScores(torch.autograd.Function):
+    """(pos_score, neg_score) of BPR triples without materialising the three [B, D] gathers (csrc/train_ops.cu)."""
+
+    @staticmethod
+    def forward(ctx, eu, ei, users, pos, neg):
+        global LAUNCHES
+        lib = _lib.load()
+        eup, ldu = _rows(eu, "eu")
+        eip, ldi = _rows(ei, "ei")
+        b, d = int(users.numel()), int(eu.shape[1])
+        ps = torch.empty(b, dtype=torch.float32, device=eu.device)
+        ns = torch.empty(b, dtype=torch.float32, device=eu.device)
+        with torch.cuda.device(eu.device):
+            _lib.check(lib.gmr_bpr_scores_f32(eup, ldu, eip, ldi, _ptr(users), _ptr(pos), _ptr(neg), b, d, _ptr(ps), _ptr(ns),
+                                              _stream()), "gmr_bpr_scores_f32")
+        LAUNCHES += 1
+        ctx.save_for_backward(eu, ei, users, pos, neg)
+        return ps, ns
+
+    @staticmethod
+    def backward(ctx, g_pos, g_neg):
+        global LAUNCHES
+        lib = _lib.load()
+        eu, ei, users, pos, neg = ctx.saved_tensors
+        eup, ldu = _rows(eu, "eu")
+        eip, ldi = _rows(ei, "ei")
+        d_eu, d_ei = torch.zeros_like(eu, memory_format=torch.contiguous_format), torch.zeros_like(ei, memory_format=torch.contiguous_format)
+        b, d = int(users.numel()), int(eu.shape[1])
+        with torch.cuda.device(eu.device):
+            _lib.check(lib.gmr_bpr_scores_backward_f32(eup, ldu, eip, ldi, _ptr(users), _ptr(pos), _ptr(neg), b, d,
+                                                       _ptr(g_pos.contiguous()), _ptr(g_neg.contiguous()), _ptr(d_eu),
+                                                       int(d_eu.stride(0)), _ptr(d_ei), int(d_ei.stride(0)), _stream()),
+                       "gmr_bpr_scores_backward_f32")
+        LAUNCHES += 1
+        return d_eu, d_ei, None, None, None
+
+
+def bpr_scores(eu, ei, users, pos, neg):
+    """``((eu[users] * ei[pos]).sum(-1), (eu[users] * ei[neg]).sum(-1))``, differentiable w.r.t. ``eu`` and ``ei``, as one
+    fused gather + dot kernel forward and one fused scatter kernel backward (the BPR terms of every model's
+    ``calculate_loss``)."""
+    def ok(t):
+        return t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and (t.shape[1] == 1 or t.stride(1) == 1)
+
+    if not (ok(eu) and ok(ei)):
+        eu, ei = eu.contiguous().float(), ei.contiguous().float()
+    idx = [t.to(torch.int64).contiguous() for t in (users, pos, neg)]
+    return _BprScores.apply(eu, ei, *idx)
+
+
 def linear_proj(x, linear):
     """``linear(x)`` for an ``nn.Linear`` with 64 outputs over a wide feature table (GUME's image/text_reduce_dim,
     gume.py:232-233; VBPR's item_linear, vbpr.py:69-75): the split-TF32 tcgen05 kernel under ``no_grad`` when the shape

@@ -216,6 +216,24 @@ int gmr_dense_proj_f32(const float* A, int64_t lda, int32_t M, int32_t K, const 
                        int64_t ldc, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Training-side fusion: the BPR gathers of calculate_loss
+ * replaces  anc = usr[users]; pos = itm[pos_items]; neg = itm[neg_items];
+ *           (anc * pos).sum(-1), (anc * neg).sum(-1)        and their index_put_(accumulate) backward
+ *   GenMMRec/src/models/diffmm.py:211-219, vbpr.py:84-93, gume.py:281-292, genrecv1.py:362-372, lightgcn.py:136-146
+ *
+ * pos_score[t] = <Eu[users[t]], Ei[pos[t]]>,  neg_score[t] = <Eu[users[t]], Ei[neg[t]]>   (fp32 fmaf chains).
+ * The backward ACCUMULATES (+=) into dEu / dEi:
+ *   dEu[users[t]] += g_pos[t] Ei[pos[t]] + g_neg[t] Ei[neg[t]];  dEi[pos[t]] += g_pos[t] Eu[users[t]];
+ *   dEi[neg[t]] += g_neg[t] Eu[users[t]]
+ * with fp32 atomic adds (repeated indices inside a batch), i.e. reproducible to summation-order rounding.
+ * ------------------------------------------------------------------------------------------- */
+int gmr_bpr_scores_f32(const float* Eu, int64_t ldu, const float* Ei, int64_t ldi, const int64_t* users, const int64_t* pos,
+                       const int64_t* neg, int32_t B, int32_t D, float* pos_score, float* neg_score, void* stream);
+int gmr_bpr_scores_backward_f32(const float* Eu, int64_t ldu, const float* Ei, int64_t ldi, const int64_t* users,
+                                const int64_t* pos, const int64_t* neg, int32_t B, int32_t D, const float* g_pos,
+                                const float* g_neg, float* dEu, int64_t lddu, float* dEi, int64_t lddi, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Peer-memory plumbing for the fused SpMM + all-gather (CUDA IPC, one process per GPU).
  * gmr_peer_alloc allocates `bytes` of device memory suitable for export; gmr_peer_export fills a
  * 64-byte handle; another process maps it with gmr_peer_open.  The Python host exchanges the
