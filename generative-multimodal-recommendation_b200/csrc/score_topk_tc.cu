@@ -23,6 +23,11 @@
 //      candidate, eps the bound above, s_K its K-th exact score): no item outside the candidate list
 //      can then reach the top K.  Uncertified rows (rare: needs >= KP - K near-ties) are queued
 //      and redone by the fp32 kernel, so both precision modes return identical results.
+//   4. wide operands (D > 256: the modality feature tables of the kNN item-item graphs, D = 4096 / 384,
+//      GenMMRec/src/utils/utils.py:147-197) do not fit a resident A' tile: in STREAM_A mode every ring stage carries
+//      one K-atom of A' AND one of B' (32 KB), both TMA-fed, and the accumulator integrates 3 D / 64 atoms per tile
+//      in TMEM -- a K-chunked GEMM with the same fused top-K epilogue.  This is the tensor-core kNN builder
+//      (SURVEY.md section 8f rank 1).
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -100,14 +105,15 @@ struct TcArgs {
     int32_t* fallback_rows;   // [B]
     int32_t* fallback_count;  // [1]
     int32_t n_stages;
+    float split_err;  // error bound of the split product, relative to |u| max|e| (grows with the accumulation length)
     uint32_t* dbg;  // misc counters
     int32_t debug;  // GMR_TC_DEBUG: 1 = epilogue only drains TMEM, 2 = filter without appends (timing experiments)
 };
 
 // dynamic shared memory layout (1024-byte aligned): A' atoms (resident per user tile) | ring of B'
 // atoms (one 128 x 64 bf16 K-atom = 16 KB per stage) | bias tile | barriers | row states
-template <int NPL, bool HAS_BIAS>
-__global__ void __launch_bounds__(kTcThreads, 2)
+template <int NPL, bool HAS_BIAS, bool STREAM_A>
+__global__ void __launch_bounds__(kTcThreads, STREAM_A ? 1 : 2)
     score_topk_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcArgs a)
 {
     constexpr int CAP = 32 * NPL;
@@ -119,9 +125,11 @@ __global__ void __launch_bounds__(kTcThreads, 2)
     const int n_atoms = (3 * a.D) / 64;                       // K' / 64
     const int n_stages = a.n_stages;
     const uint32_t atom_a_bytes = kTM * 128, atom_b_bytes = kTN * 128;
+    // resident mode: A' atoms | ring of B' atoms.  STREAM_A: ring of (A' atom | B' atom) pairs.
+    const uint32_t stage_bytes = STREAM_A ? (atom_a_bytes + atom_b_bytes) : atom_b_bytes;
     uint8_t* sm_a = smem_raw;
-    uint8_t* sm_b = sm_a + (size_t)n_atoms * atom_a_bytes;    // [n_stages][kTN * 128 B]
-    uint8_t* tail = sm_b + (size_t)n_stages * atom_b_bytes;
+    uint8_t* sm_b = STREAM_A ? smem_raw : sm_a + (size_t)n_atoms * atom_a_bytes;   // ring base
+    uint8_t* tail = sm_b + (size_t)n_stages * stage_bytes;
     float* sm_bias = reinterpret_cast<float*>(tail);          // [2][kTN]
     uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 2 * kTN * sizeof(float));
     uint64_t* full_b = bars;                    // [kMaxStages]
@@ -169,15 +177,22 @@ __global__ void __launch_bounds__(kTcThreads, 2)
             int stage = 0;
             uint32_t phase = 0, a_phase = 0;
             for (int ut = blockIdx.x; ut < n_utiles; ut += gridDim.x) {
-                mbar_wait(a_empty, a_phase ^ 1);  // first pass: passes immediately (fresh barrier)
-                mbar_expect_tx(a_full, (uint32_t)n_atoms * atom_a_bytes);
-                for (int k = 0; k < n_atoms; ++k) tma_load_2d(sm_a + (size_t)k * atom_a_bytes, &map_a, a_full, k * 64, ut * kTM);
-                a_phase ^= 1;
+                if (!STREAM_A) {
+                    mbar_wait(a_empty, a_phase ^ 1);  // first pass: passes immediately (fresh barrier)
+                    mbar_expect_tx(a_full, (uint32_t)n_atoms * atom_a_bytes);
+                    for (int k = 0; k < n_atoms; ++k) tma_load_2d(sm_a + (size_t)k * atom_a_bytes, &map_a, a_full, k * 64, ut * kTM);
+                    a_phase ^= 1;
+                }
                 for (int it = 0; it < n_itiles; ++it) {
                     for (int k = 0; k < n_atoms; ++k) {
                         mbar_wait(&empty_b[stage], phase ^ 1);
-                        mbar_expect_tx(&full_b[stage], atom_b_bytes);
-                        tma_load_2d(sm_b + (size_t)stage * atom_b_bytes, &map_b, &full_b[stage], k * 64, it * kTN);
+                        mbar_expect_tx(&full_b[stage], stage_bytes);
+                        uint8_t* sb = sm_b + (size_t)stage * stage_bytes;
+                        if (STREAM_A) {
+                            tma_load_2d(sb, &map_a, &full_b[stage], k * 64, ut * kTM);
+                            sb += atom_a_bytes;
+                        }
+                        tma_load_2d(sb, &map_b, &full_b[stage], k * 64, it * kTN);
                         if (++stage == n_stages) {
                             stage = 0;
                             phase ^= 1;
@@ -193,20 +208,23 @@ __global__ void __launch_bounds__(kTcThreads, 2)
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0, a_phase = 0;
             for (int ut = blockIdx.x; ut < n_utiles; ut += gridDim.x) {
-                mbar_wait(a_full, a_phase);
-                a_phase ^= 1;
+                if (!STREAM_A) {
+                    mbar_wait(a_full, a_phase);
+                    a_phase ^= 1;
+                }
                 for (int it = 0; it < n_itiles; ++it) {
                     mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)acc * kTN;
-                    const uint32_t a_base = smem_u32(sm_a);
                     for (int k = 0; k < n_atoms; ++k) {
                         mbar_wait(&full_b[stage], phase);
                         tc_fence_after();
-                        const uint32_t b_base = smem_u32(sm_b + (size_t)stage * atom_b_bytes);
+                        const uint32_t st_base = smem_u32(sm_b + (size_t)stage * stage_bytes);
+                        const uint32_t a_atom = STREAM_A ? st_base : smem_u32(sm_a) + k * atom_a_bytes;
+                        const uint32_t b_base = STREAM_A ? st_base + atom_a_bytes : st_base;
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {  // 4 x (K = 16 bf16 = 32 B) per 128-byte swizzle row
-                            const uint64_t ad = umma_desc_sw128(a_base + k * atom_a_bytes + kk * 32);
+                            const uint64_t ad = umma_desc_sw128(a_atom + kk * 32);
                             const uint64_t bd = umma_desc_sw128(b_base + kk * 32);
                             tc_mma_bf16(d_tmem, ad, bd, idesc, (k | kk) ? 1u : 0u);
                         }
@@ -222,7 +240,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
                         acc_phase ^= 1;
                     }
                 }
-                tc_commit(a_empty);  // A' tile free once every MMA of this user tile retired
+                if (!STREAM_A) tc_commit(a_empty);  // A' tile free once every MMA of this user tile retired
             }
         }
     } else {
@@ -388,7 +406,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
                 }
                 bool certified = true;
                 if (n_cand >= KP) {  // otherwise every item that could matter is in the list
-                    const float eps = kSplitErr * a.a_norm[rb] * b_max + 4.8e-7f * fabsf(t_approx);
+                    const float eps = a.split_err * a.a_norm[rb] * b_max + 4.8e-7f * fabsf(t_approx);
                     certified = (kth_key != 0ull) && (t_approx + eps < key_score(kth_key));
                 }
 #pragma unroll
@@ -450,12 +468,18 @@ static bool make_map(CUtensorMap* m, void* base, int64_t rows, int64_t kd, int b
 static int tc_stages_for(int32_t D);
 static int tc_kp(int32_t K) { return K + 8 <= 64 ? 64 : (K + 8 <= 128 ? 128 : 256); }
 
-bool score_tc_supported(int32_t D, int32_t K) { return D % 64 == 0 && D >= 64 && D <= 256 && K + 8 <= 256 && tc_stages_for(D) >= 2; }
+constexpr int32_t kTcMaxD = 8192;     // widest operand of the streamed (K-chunked) mode
+constexpr int32_t kTcResidentD = 256; // up to here the A' tile stays resident in shared memory
+static bool tc_stream(int32_t D) { return D > kTcResidentD; }
 
-static int tc_grid(int32_t B)
+bool score_tc_supported(int32_t D, int32_t K) { return D % 64 == 0 && D >= 64 && D <= kTcMaxD && K + 8 <= 256 && tc_stages_for(D) >= 2; }
+
+static bool tc_stream(int32_t D);
+static int tc_grid(int32_t B, int32_t D)
 {
     const int tiles = (B + kTM - 1) / kTM;
-    return tiles < 2 * sm_count() ? tiles : 2 * sm_count();
+    const int cap = (tc_stream(D) ? 1 : 2) * sm_count();   // resident CTAs per SM: 1 in the streamed mode
+    return tiles < cap ? tiles : cap;
 }
 
 struct TcLayout {
@@ -480,7 +504,7 @@ static TcLayout tc_layout(int32_t B, int32_t I, int32_t D, int32_t K)
     L.a_norm = take((int64_t)L.b_pad * 4);
     L.misc = take(256);  // [0] max item norm bits, [1] fallback count
     L.fallback = take((int64_t)B * 4);
-    L.slots = take((int64_t)tc_grid(B) * kTM * cap * 8);
+    L.slots = take((int64_t)tc_grid(B, D) * kTM * cap * 8);
     L.simt = take(score_simt_workspace_bytes(B, K));
     L.total = off;
     return L;
@@ -491,12 +515,16 @@ int64_t score_tc_workspace_bytes(int32_t B, int32_t I, int32_t D, int32_t K) { r
 
 static size_t tc_smem_fixed(int32_t D)
 {
-    const int n_atoms = 3 * D / 64;
+    const int n_atoms = tc_stream(D) ? 0 : 3 * D / 64;   // streamed mode keeps no resident A' tile
     return (size_t)n_atoms * kTM * 128 + 2 * kTN * sizeof(float) + (2 * kMaxStages + 8) * sizeof(uint64_t) +
            kTM * sizeof(RowState) + 1024;
 }
 static int tc_stages(int32_t D)
 {
+    if (tc_stream(D)) {  // one CTA per SM, ring of (A' atom | B' atom) pairs
+        const int s = (int)(((int64_t)227 * 1024 - (int64_t)tc_smem_fixed(D)) / ((kTM + kTN) * 128));
+        return s > kMaxStages ? kMaxStages : s;
+    }
     // two CTAs per SM when they fit (D = 64): 8 epilogue warps per SM hide each other's latencies and
     // the two MMA streams share the tensor pipe; otherwise one CTA with a deep ring
     int64_t room = (int64_t)113 * 1024 - (int64_t)tc_smem_fixed(D);
@@ -537,7 +565,8 @@ int score_topk_tc_launch(const float* Eu, int64_t lde_u, const int64_t* users, i
         set_error("score_topk_tc: D=%d leaves no room for the operand ring in shared memory", D);
         return GMR_ERR_UNSUPPORTED;
     }
-    const size_t smem = tc_smem_fixed(D) + (size_t)n_stages * kTN * 128;
+    const bool stream = tc_stream(D);
+    const size_t smem = tc_smem_fixed(D) + (size_t)n_stages * (stream ? (kTM + kTN) * 128 : kTN * 128);
     uint8_t* ws = (uint8_t*)workspace;
     __nv_bfloat16* a_split = (__nv_bfloat16*)(ws + L.a_split);
     __nv_bfloat16* b_split = (__nv_bfloat16*)(ws + L.b_split);
@@ -562,20 +591,25 @@ int score_topk_tc_launch(const float* Eu, int64_t lde_u, const int64_t* users, i
     a.mask_rowptr = mask_rowptr; a.mask_items = mask_items; a.K = K; a.out_ids = out_ids; a.out_scores = out_scores;
     a.slots = (uint64_t*)(ws + L.slots); a.a_norm = a_norm; a.b_max_norm_bits = misc;
     a.fallback_rows = fallback; a.fallback_count = (int32_t*)(misc + 1); a.n_stages = n_stages;
+    // split error: 3 dropped 2^-16 terms (+5 %) and, for long accumulations, the worst-case fp32 summation error of the
+    // 3 D products; D <= 256 keeps the constant its certification tests were run with
+    a.split_err = stream ? (4.8e-5f + 3.0f * (float)D * 5.97e-8f) : kSplitErr;
     a.dbg = misc;
     a.debug = getenv("GMR_TC_DEBUG") ? atoi(getenv("GMR_TC_DEBUG")) : 0;
-    const int grid = tc_grid(B);
+    const int grid = tc_grid(B, D);
     const int kp = tc_kp(K);
+#define GMR_TC_LAUNCH1(NPL, BIAS, STREAM)                                                                          \
+    do {                                                                                                           \
+        GMR_CHECK_CUDA(cudaFuncSetAttribute(score_topk_tc_kernel<NPL, BIAS, STREAM>,                               \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+        score_topk_tc_kernel<NPL, BIAS, STREAM><<<grid, kTcThreads, smem, st>>>(map_a, map_b, a);                  \
+    } while (0)
 #define GMR_TC_LAUNCH(NPL)                                                                                         \
     do {                                                                                                           \
-        if (bias != nullptr) {                                                                                     \
-            GMR_CHECK_CUDA(cudaFuncSetAttribute(score_topk_tc_kernel<NPL, true>,                                   \
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
-            score_topk_tc_kernel<NPL, true><<<grid, kTcThreads, smem, st>>>(map_a, map_b, a);                      \
+        if (stream) {                                                                                              \
+            if (bias != nullptr) GMR_TC_LAUNCH1(NPL, true, true); else GMR_TC_LAUNCH1(NPL, false, true);           \
         } else {                                                                                                   \
-            GMR_CHECK_CUDA(cudaFuncSetAttribute(score_topk_tc_kernel<NPL, false>,                                  \
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
-            score_topk_tc_kernel<NPL, false><<<grid, kTcThreads, smem, st>>>(map_a, map_b, a);                     \
+            if (bias != nullptr) GMR_TC_LAUNCH1(NPL, true, false); else GMR_TC_LAUNCH1(NPL, false, false);         \
         }                                                                                                          \
     } while (0)
     if (kp == 64)
@@ -585,6 +619,7 @@ int score_topk_tc_launch(const float* Eu, int64_t lde_u, const int64_t* users, i
     else
         GMR_TC_LAUNCH(32);
 #undef GMR_TC_LAUNCH
+#undef GMR_TC_LAUNCH1
     GMR_LAUNCH_CHECK();
     // uncertified rows: exact fp32 kernel, row count read on the device (no host synchronisation)
     score_simt_set_dynamic_rows((const int32_t*)(misc + 1));

@@ -121,11 +121,14 @@ def knn_graph_dense(feat, k, eps_normalize=False):
     return knn_from_topk(val, ind)
 
 
-def knn_graph_fused(feat, k, eps_normalize=False, precision="fp32"):
-    """kNN graph WITHOUT the dense I x I similarity matrix: the fused score + top-K kernel (K2) run
+def knn_graph_fused(feat, k, eps_normalize=False, precision="auto"):
+    """kNN graph WITHOUT the dense I x I similarity matrix: the fused score + top-K kernel (K2/K3) run
     on the row-normalised features against themselves.  Neighbour
     order is (similarity desc, item id asc); similarities are the fp32 FMA chain of the kernel, so
-    weights agree with the dense builder to ~1e-6 relative and neighbour sets up to exact ties."""
+    weights agree with the dense builder to ~1e-6 relative and neighbour sets up to exact ties.
+    ``precision='auto'`` takes the tensor cores whenever the feature width is a multiple of 64 (the 4096-d image and
+    384-d text tables are): the K-chunked split-bf16 tcgen05 product with exact fp32 re-scoring of the candidates
+    (csrc/score_topk_tc.cu, STREAM_A); every precision returns the same ids and similarities."""
     from . import ops
 
     feat = feat.to(torch.float32)

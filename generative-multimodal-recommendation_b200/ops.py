@@ -454,8 +454,8 @@ def linear_proj(x, linear):
 
 def tc_supported(d, k, precision="tc"):
     """Shapes the tcgen05 scoring paths accept (operand tiles + ring stages must fit in shared memory)."""
-    if precision == "tc_split":
-        return d % 64 == 0 and 64 <= d <= 192 and k <= 248
+    if precision == "tc_split":   # D > 256 runs K-chunked: both operands streamed, accumulation over 3 D / 64 atoms in TMEM
+        return d % 64 == 0 and 64 <= d <= 8192 and k <= 248
     return d % 64 == 0 and 64 <= d <= 256 and k <= 256
 
 
@@ -472,8 +472,9 @@ def score_mask_topk(eu, ei, k, users=None, bias=None, mask_rowptr=None, mask_ite
     """
     global LAUNCHES
     lib = _lib.load()
-    if precision == "auto":  # tensor cores whenever the shape is supported; both paths return the same result
-        precision = "tc" if tc_supported(int(ei.shape[1]), k) else "fp32"
+    if precision == "auto":  # tensor cores whenever the shape is supported; every path returns the same result
+        dd = int(ei.shape[1])
+        precision = "tc" if tc_supported(dd, k) else ("tc_split" if tc_supported(dd, k, "tc_split") else "fp32")
     mode = _PRECISIONS[precision]
     eup, lde_u = _rows(eu, "eu")
     eip, lde_i = _rows(ei, "ei")
