@@ -53,6 +53,10 @@ def main():
         "iu[I x U] D=64": (adj.iu, torch.randn(nu, d, device=dev), 64),
         "ui[U x I] D=128": (adj.ui, torch.randn(ni, 2 * d, device=dev), 128),
     }
+    m = wl.model
+    w0, w1 = m._modal_weights_host()
+    mix = m._modal_mix_graph(m.image_UI_matrix, m.text_UI_matrix, w0, w1)
+    cases["mix[N x N] D=64"] = (mix, torch.randn(n, d, device=dev), 64)   # ~5 nonzeros per row
     os.environ["GMR_SPMM_BLOCKED"] = "0"
     keep = args.cases.split(",")
     for name, (g, x, dd) in cases.items():
