@@ -162,3 +162,72 @@ def test_popularity_groups_follow_quick_start():
     assert counts[pop].min() >= counts[rest].max()
     ucounts = np.bincount(tr.users.numpy(), minlength=500)
     assert cfg["warm_users"] == set(np.flatnonzero(ucounts > 5).tolist())
+
+
+def test_early_stopping_and_train_loader_negatives(toy_data):
+    """Host logic of the training loop (GenMMRec/src/utils/utils.py:70-113, utils/dataloader.py:226-275): the early-stopping
+    rule, and one uniform negative per row that is never in the user's train history."""
+    from genmmrec_b200.common.trainer import Trainer
+    es = Trainer.early_stopping
+    assert es(0.5, 0.4, 3, 2) == (0.5, 0, False, True)            # improved: counter resets
+    assert es(0.3, 0.4, 1, 2) == (0.4, 2, False, False)           # not improved, still within patience
+    assert es(0.3, 0.4, 2, 2) == (0.4, 3, True, False)            # patience exceeded
+    assert es(0.3, 0.4, 0, 2, bigger=False) == (0.3, 0, False, True)
+    cfg = Config("LightGCN", "toy", {"device": "cpu", "is_multimodal_model": False})
+    tr, _, _ = toy_splits(cfg, toy_data)
+    loader = TrainDataLoader(cfg, tr, batch_size=256, shuffle=True)
+    hist = set(zip(tr.users.tolist(), tr.items.tolist()))
+    seen = 0
+    for inter in loader:
+        assert inter.shape[0] == 3 and inter.dtype == torch.int64
+        u, p, n = inter.tolist()
+        assert all((a, b) in hist for a, b in zip(u, p))          # positives are train interactions
+        assert not any((a, b) in hist for a, b in zip(u, n))      # negatives never are
+        seen += len(u)
+    assert seen == len(tr)
+
+
+def test_device_edge_extraction_equals_reference_loop():
+    """DiffMM.edges_from_denoised (vectorised) against the per-element loop of common/trainer.py:548-553, on CPU tensors."""
+    from genmmrec_b200.models.diffmm import DiffMM
+    g = torch.Generator().manual_seed(5)
+    batch_index = torch.randperm(300, generator=g)[:17]
+    den = torch.randn(17, 40, generator=g)
+    u, i = DiffMM.edges_from_denoised(batch_index, den, 4)
+    _, idx = torch.topk(den, k=4)
+    u_ref = [int(batch_index[a]) for a in range(17) for _ in range(4)]
+    i_ref = [int(idx[a][b]) for a in range(17) for b in range(4)]
+    assert u.tolist() == u_ref and i.tolist() == i_ref
+
+
+def test_blocked_spmm_dispatch_policy(monkeypatch):
+    """ops._block_cols_for: K1b is opt-in; `auto` blocks only tables beyond GMR_SPMM_BLOCK_MIN_MB; the slice size follows
+    GMR_SPMM_BLOCK_MB; unaligned operands and widths that are not multiples of 4 stay on K1."""
+    from genmmrec_b200 import ops
+
+    class G:
+        shape = (1000, 2_000_000)
+
+    class T:
+        def __init__(self, rows, stride, ptr=256):
+            self.shape, self._s, self._p = (rows, 64), stride, ptr
+
+        def stride(self, k):
+            return self._s
+
+        def data_ptr(self):
+            return self._p
+
+    x, y = T(2_000_000, 64), T(1000, 64)
+    monkeypatch.delenv("GMR_SPMM_BLOCKED", raising=False)
+    assert ops._block_cols_for(G, 64, x, y) is None                      # default: row-centric K1
+    monkeypatch.setenv("GMR_SPMM_BLOCKED", "auto")
+    assert ops._block_cols_for(G, 64, x, y) == (48 << 20) // 256          # 512 MB table: 48 MB slices
+    monkeypatch.setenv("GMR_SPMM_BLOCK_MB", "32")
+    assert ops._block_cols_for(G, 64, x, y) == (32 << 20) // 256
+    assert ops._block_cols_for(G, 62, x, y) is None                       # width not a multiple of 4
+    assert ops._block_cols_for(G, 64, T(2_000_000, 64, ptr=260), y) is None   # misaligned X
+    G.shape = (1000, 100_000)                                             # 25.6 MB table: below the 96 MB threshold
+    assert ops._block_cols_for(G, 64, x, y) is None
+    monkeypatch.setenv("GMR_SPMM_BLOCKED", "1")
+    assert ops._block_cols_for(G, 64, x, y) == 100_000                    # forced: one block covers the table
