@@ -31,6 +31,8 @@ class GenRecV1(GeneralRecommender):
         self.rebuild_k = config["rebuild_k"]
         self.knn_k = config["knn_k"]
         self.reg_weight = config["reg_weight"]
+        self.ssl_reg1, self.ssl_reg2 = config["ssl_reg1"] or 0.0, config["ssl_reg2"] or 0.0
+        self.temp = config["temperature"] or 1.0
         self.knn_builder = config["knn_builder"] or "fused"
         self.image_embedding = self.v_feat
         self.text_embedding = self.t_feat
@@ -147,15 +149,29 @@ class GenRecV1(GeneralRecommender):
         c = self.content_embedding(self.norm_adj, self.image_UI_matrix)
         return c[:self.n_users], c[self.n_users:]
 
+    @staticmethod
+    def infoNCE_loss(view1, view2, temperature):
+        """In-batch InfoNCE of genrecv1.py:408-415: -log( exp(<a_i, b_i> / T) / sum_j exp(<a_i, b_j> / T) ), rows normalised."""
+        a, b = F.normalize(view1, dim=1), F.normalize(view2, dim=1)
+        pos = torch.exp(torch.sum(a * b, dim=-1) / temperature)
+        tot = torch.exp(a @ b.t() / temperature).sum(dim=1)
+        return -torch.log(pos / tot).mean()
+
     def calculate_loss(self, interaction):
-        """BPR + L2 terms of genrecv1.py:355-401 on the content embedding (the InfoNCE terms need the
-        side branch and are training-only extras outside the hot path)."""
+        """BPR + L2 + the item-item and user-item contrastive terms of genrecv1.py:355-401 (content vs side embedding);
+        every graph product goes through the differentiable ``ops.spmm``, the BPR gathers through the fused kernel."""
         users, pos_items, neg_items = interaction[0], interaction[1], interaction[2]
         if self.image_UI_matrix is None:
             return torch.tensor(0.0, requires_grad=True).to(self.device)
-        c = self.content_embedding(self.norm_adj, self.image_UI_matrix)
-        ue, ie = c[:self.n_users], c[self.n_users:]
+        if self.image_II_matrix is None or self.text_II_matrix is None:
+            self.build_item_item_matrices()       # the reference's trainer builds them once (common/trainer.py:676-687)
+        nu = self.n_users
+        content, side = self.forward(self.R, self.norm_adj, self.image_UI_matrix, self.image_II_matrix, self.text_II_matrix)
+        ue, ie = content[:nu], content[nu:]
+        su, si = side[:nu], side[nu:]
         ps, ns = bpr_scores(ue, ie, users, pos_items, neg_items)   # fused gather + dot (csrc/train_ops.cu)
         bpr = -torch.mean(F.logsigmoid(ps - ns))
-        reg = self.user_embedding.weight.norm(2).square() + self.item_id_embedding.weight.norm(2).square()
-        return bpr + reg * self.reg_weight
+        reg = (self.user_embedding.weight.norm(2).square() + self.item_id_embedding.weight.norm(2).square()) * self.reg_weight
+        cl1 = self.infoNCE_loss(si[pos_items], ie[pos_items], self.temp) + self.infoNCE_loss(su[users], ue[users], self.temp)
+        cl2 = self.infoNCE_loss(ue[users], ie[pos_items], self.temp) + self.infoNCE_loss(ue[users], si[pos_items], self.temp)
+        return bpr + reg + cl1 * self.ssl_reg1 + cl2 * self.ssl_reg2

@@ -84,6 +84,55 @@ def test_diffmm_loss_gradients_match_reference_port(env):  # noqa: F811
         assert float((got[n] - p[n].grad).abs().max()) <= 2e-4 * scale + 1e-9, n
 
 
+def test_genrecv1_loss_matches_reference_port(env):  # noqa: F811
+    """GenRecV1.calculate_loss (BPR + L2 + four in-batch InfoNCE terms over the content / side embeddings,
+    genrecv1.py:355-415) against the CPU restatement under autograd: loss value and embedding gradients."""
+    z, meta = load_golden("toy_genrecv1")
+    data = toy_arrays()
+    cfg, model, loaders = build(env, "GenRecV1", meta, data, "toy")
+    load_params(model, golden_params(z))
+    set_graphs(env, "GenRecV1", model, meta, data)
+    model.eval()   # BatchNorm / Dropout in inference mode on both sides (the port restates eval-mode layers)
+    rng = np.random.default_rng(1)
+    b = 256
+    inter = torch.from_numpy(np.stack([rng.integers(0, data["n_users"], b), rng.integers(0, data["n_items"], b),
+                                       rng.integers(0, data["n_items"], b)])).to(model.device)
+    loss = model.calculate_loss(inter)
+    loss.backward()
+    names = ["user_embedding.weight", "item_id_embedding.weight"]
+    got = {"user_embedding.weight": model.user_embedding.weight.grad.detach().cpu(),
+           "item_id_embedding.weight": model.item_id_embedding.weight.grad.detach().cpu()}
+    p = {k: v.detach().cpu().clone().requires_grad_(k in names) for k, v in model.state_dict().items()}
+
+    def coo(gr):
+        t = gr.to_torch_coo()
+        return torch.sparse_coo_tensor(t._indices().cpu(), t._values().cpu(), t.shape)
+
+    from genmmrec_b200.models._common import as_graph
+    c = meta["config"]
+    nu = data["n_users"]
+    ue, ie = rp.genrecv1_content(p, coo(as_graph(model.norm_adj)), coo(model.image_UI_matrix), nu, c["n_layers"])
+    side = rp.genrecv1_side(p, torch.cat([ue, ie]), coo(model.R), coo(model.image_II_matrix), coo(model.text_II_matrix),
+                            model.image_embedding.cpu(), model.text_embedding.cpu(), c["n_layers"])
+    su, si = side[:nu], side[nu:]
+    u, pi, ni = inter.cpu()
+    F = torch.nn.functional
+
+    def nce(a, bb, t):
+        a, bb = F.normalize(a, dim=1), F.normalize(bb, dim=1)
+        return -torch.log(torch.exp((a * bb).sum(-1) / t) / torch.exp(a @ bb.t() / t).sum(1)).mean()
+
+    ref = -torch.mean(F.logsigmoid((ue[u] * ie[pi]).sum(-1) - (ue[u] * ie[ni]).sum(-1))) \
+        + (p[names[0]].norm(2).square() + p[names[1]].norm(2).square()) * model.reg_weight \
+        + (nce(si[pi], ie[pi], model.temp) + nce(su[u], ue[u], model.temp)) * model.ssl_reg1 \
+        + (nce(ue[u], ie[pi], model.temp) + nce(ue[u], si[pi], model.temp)) * model.ssl_reg2
+    ref.backward()
+    assert abs(float(loss) - float(ref)) <= 2e-5 * abs(float(ref))
+    for n in names:
+        scale = float(p[n].grad.abs().max())
+        assert float((got[n] - p[n].grad).abs().max()) <= 5e-4 * scale + 1e-9, n
+
+
 def test_forward_cl_mm_multi_rhs_equals_per_view_chains(env):  # noqa: F811
     z, meta = load_golden("toy_diffmm")
     data = toy_arrays()
