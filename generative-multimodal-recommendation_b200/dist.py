@@ -399,7 +399,9 @@ class ShardedGCNChain(object):
         U0, I0 = self.embeddings_fn()
         e0 = torch.cat([U0.detach(), I0.detach()])
         out_u = out_i = None
-        for graph, w in zip(self.graphs_fn(), self.weights_fn()):
+        weights = self.weights_fn()   # python floats, or a device tensor (no host read: the step is graph-capturable)
+        for gi, graph in enumerate(self.graphs_fn()):
+            w = weights[gi]
             g_u, g_i = self._row_blocks(graph)
             acc_u, acc_i = e0[self.u0:self.u1].clone(), e0[nu + self.i0:nu + self.i1].clone()
             full = e0
@@ -413,9 +415,13 @@ class ShardedGCNChain(object):
                     rows_push(last_i, self.layer_all.ptr_table, W, nu + self.i0, d)
                     stream_barrier(self.token)
                     full = self.layer_all.tensor
-            scale = float(w) / float(self.n_layers + 1)
-            out_u = acc_u * scale if out_u is None else out_u + acc_u * scale
-            out_i = acc_i * scale if out_i is None else out_i + acc_i * scale
+            if torch.is_tensor(w):   # same operation order as the single-GPU model: w_g * (sum / (L + 1))
+                term_u, term_i = w * (acc_u / float(self.n_layers + 1)), w * (acc_i / float(self.n_layers + 1))
+            else:
+                scale = float(w) / float(self.n_layers + 1)
+                term_u, term_i = acc_u * scale, acc_i * scale
+            out_u = term_u if out_u is None else out_u + term_u
+            out_i = term_i if out_i is None else out_i + term_i
             stream_barrier(self.token)           # the next graph's chain reuses the layer buffer
         return out_u, out_i
 
@@ -436,8 +442,7 @@ def sharded_genrecv1(model, group=None):
     import torch.nn.functional as F
 
     def weights():
-        w = F.softmax(torch.stack([model.origin_weight.detach(), model.generation_weight.detach()]).flatten(), dim=0)
-        return [float(x) for x in w.tolist()]
+        return F.softmax(torch.stack([model.origin_weight.detach(), model.generation_weight.detach()]).flatten(), dim=0)
 
     from .models._common import as_graph
     return ShardedGCNChain(model, lambda: [as_graph(model.norm_adj), as_graph(model.image_UI_matrix)], weights,

@@ -10,8 +10,11 @@ Three pieces of this model sit on the accelerated path:
   * ``CNet.output_proj`` (ld4mrec.py:36,54), the score contraction ``[B, hidden] x [hidden, n_items]
     + bias`` -> fused with masking and top-K (K2 with a bias vector).
 The small conditional residual blocks in between stay in torch.  The SVD user encoder
-(ld4mrec.py:138-159) and the diffusion training loss are outside the hot path: ``user_svd_emb`` is a
-buffer the caller may overwrite (it is computed with the same scipy call by default).
+(ld4mrec.py:138-159) is outside the hot path: ``user_svd_emb`` is a buffer the caller may overwrite (it is
+computed with the same scipy call by default).  ``calculate_loss`` is the reference's diffusion objective
+(ld4mrec.py:265-344) kept on the device end to end: history rows expanded from the CSR with one scatter instead
+of a host scipy slice + upload, steps drawn with ``torch.multinomial`` from the device-resident loss history,
+and the history's per-sample moving average applied in closed form instead of a ``.item()`` loop.
 """
 import numpy as np
 import torch
@@ -81,6 +84,10 @@ class LD4MRec(GeneralRecommender):
         cond_dim = self.svd_k + (self.embedding_size if self.mm_dim > 0 else 0)
         self.cnet = CNet(self.n_items, self.cnet_hidden, cond_dim, self.cnet_layers, config["dropout"] or 0.1)
         self.time_emb_dim = self.cnet_hidden
+        self.steps = int(config["steps"] or 100)
+        self.smoothing_gamma = float(config["smoothing_gamma"] if config["smoothing_gamma"] is not None else 0.1)
+        self.register_buffer("loss_history", torch.ones(self.steps))   # importance sampling of the diffusion step
+        self._init_noise_schedule(float(config["min_noise_level"] if config["min_noise_level"] is not None else 0.001))
         self.t_in = nn.Parameter(torch.zeros(1))
 
     def _init_svd(self):
@@ -100,6 +107,64 @@ class LD4MRec(GeneralRecommender):
             rn = gb.ld4mrec_rnorm(m.row, m.col, self.n_users, self.n_items, device=self.device)
             self.R_norm = GraphCSR.from_coo(*rn, self.device)
             self.user_mm_emb = spmm_raw(self.R_norm, torch.cat(feats, dim=1).contiguous())
+
+    def _init_noise_schedule(self, alpha_min):
+        """ld4mrec.py:208-239: 1 - alpha_bar_t linear in t, betas clamped to [1e-4, 0.9999], alpha_bar = cumprod."""
+        t = torch.arange(1, self.steps + 1, dtype=torch.float32, device=self.device)
+        alpha_bar = 1 - (alpha_min + (t - 1) / (self.steps - 1) * (1 - alpha_min))
+        ratio = alpha_bar / torch.cat([torch.ones(1, device=self.device), alpha_bar[:-1]])
+        self.betas = torch.clamp(1 - ratio, min=0.0001, max=0.9999)
+        self.alphas = 1 - self.betas
+        self.alpha_bar = torch.cumprod(self.alphas, dim=0)
+
+    def history_rows(self, user):
+        """Dense binary train rows [B, n_items] of ``user`` expanded from the device CSR (ld4mrec.py:283-292 slices a
+        scipy CSR on the host and uploads the result)."""
+        rp, col = self.R.rowptr.to(torch.int64), self.R.col.to(torch.int64)
+        user = user.to(torch.int64)
+        lens = rp[user + 1] - rp[user]
+        starts = torch.cumsum(lens, 0) - lens
+        rows = torch.repeat_interleave(torch.arange(user.numel(), device=user.device), lens)
+        src = torch.repeat_interleave(rp[user] - starts, lens) + torch.arange(rows.numel(), device=user.device)
+        x = torch.zeros(user.numel(), self.n_items, device=user.device)
+        x[rows, col[src]] = 1.0
+        return x
+
+    def q_sample(self, x_start, t, noise=None):
+        noise = torch.randn_like(x_start) if noise is None else noise
+        ab = self.alpha_bar[t].unsqueeze(1)
+        return torch.sqrt(ab) * x_start + torch.sqrt(1 - ab) * noise, noise
+
+    @torch.no_grad()
+    def _update_loss_history(self, t, losses):
+        """h[s] <- 0.9 h[s] + 0.1 loss_i applied once per sample in batch order (ld4mrec.py:338-342), in closed form:
+        a step drawn m times ends at 0.9^m h + 0.1 * sum_j 0.9^(m-1-j) loss_j (j = order of appearance)."""
+        order = torch.argsort(t, stable=True)
+        ts, ls = t[order], losses[order].to(torch.float32)
+        counts = torch.bincount(ts, minlength=self.steps)
+        first = torch.cumsum(counts, 0) - counts
+        rank = torch.arange(ts.numel(), device=t.device) - first[ts]
+        w = 0.1 * torch.pow(torch.full_like(ls, 0.9), (counts[ts] - 1 - rank).to(torch.float32))
+        add = torch.zeros_like(self.loss_history).index_add_(0, ts, w * ls)
+        self.loss_history.mul_(torch.pow(torch.full_like(self.loss_history, 0.9), counts.to(torch.float32))).add_(add)
+
+    def calculate_loss(self, interaction, t=None, noise=None):
+        """Diffusion objective of ld4mrec.py:265-344: importance-sampled step, q-sample of the history row, x0 prediction
+        by the C-Net, MSE against the label-smoothed history.  ``t`` / ``noise`` may be supplied for reproducibility."""
+        user = interaction[0]
+        x_in = self.history_rows(user)
+        gamma = self.smoothing_gamma
+        target = x_in * (1 - gamma) + (1 - x_in) * gamma
+        if t is None:
+            probs = torch.sqrt(self.loss_history ** 2)
+            t = torch.multinomial(probs / probs.sum(), user.numel(), replacement=True)
+        x_t, _ = self.q_sample(x_in, t, noise)
+        u_mm = self.mm_project(self.user_mm_emb[user]) if self.mm_project is not None else None
+        cond = torch.cat([self.user_svd_emb[user], u_mm], dim=1) if u_mm is not None else self.user_svd_emb[user]
+        pred = self.cnet(x_t, self.get_time_embedding(t), cond)
+        loss = F.mse_loss(pred, target, reduction="none").mean(dim=1)
+        self._update_loss_history(t, loss.detach())
+        return loss.mean()
 
     def get_time_embedding(self, timesteps):
         half = self.time_emb_dim // 2

@@ -23,7 +23,13 @@ def _run(model, shape, nproc, port, layers=2):
            "127.0.0.1", "--master-port", str(port), os.path.join(REPO, "tools", "dist_check.py"), "--model", model, "--shape",
            shape, "--layers", str(layers)]
     p = subprocess.run(cmd, cwd=REPO, capture_output=True, text=True, timeout=900)
-    rows = [json.loads(ln) for ln in p.stdout.splitlines() if ln.startswith("{")]
+    rows, dec = [], json.JSONDecoder()
+    for ln in p.stdout.splitlines():      # tolerate two ranks' records landing on one line
+        pos = ln.find("{")
+        while pos >= 0:
+            obj, end = dec.raw_decode(ln, pos)
+            rows.append(obj)
+            pos = ln.find("{", end)
     assert p.returncode == 0, "dist_check failed:\n%s\n%s" % (p.stdout[-3000:], p.stderr[-3000:])
     assert len(rows) == nproc
     return rows
@@ -34,7 +40,7 @@ def test_sharded_equals_single_gpu(model, shape):
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs at least two GPUs")
     nproc = 2
-    rows = _run(model, shape, nproc, 29541 + abs(hash(model)) % 50)
+    rows = _run(model, shape, nproc, {"DiffMM": 29541, "GenRecV1": 29557, "LightGCN": 29573}[model])
     for r in rows:
         # the sharded dataflow runs the same kernels on row blocks: rows are bit-identical in practice
         assert r["user_rows_rel_err"] == 0.0 and r["gathered_items_rel_err"] == 0.0, r

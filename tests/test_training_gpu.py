@@ -133,6 +133,46 @@ def test_genrecv1_loss_matches_reference_port(env):  # noqa: F811
         assert float((got[n] - p[n].grad).abs().max()) <= 5e-4 * scale + 1e-9, n
 
 
+def test_ld4mrec_diffusion_loss_matches_reference_port(env):  # noqa: F811
+    """LD4MRec.calculate_loss (ld4mrec.py:265-344) with the random draws fixed: device-built history rows, q-sample,
+    C-Net x0 prediction, label-smoothed MSE, and the closed-form loss-history update, against the CPU restatement
+    (which updates the history one sample at a time like the reference)."""
+    z, meta = load_golden("toy_ld4mrec")
+    data = toy_arrays()
+    cfg, model, loaders = build(env, "LD4MRec", meta, data, "toy")
+    load_params(model, golden_params(z))
+    model.user_svd_emb = torch.from_numpy(z["buf/user_svd_emb"]).to(model.device)
+    model.eval()                       # dropout off on both sides
+    nu, ni = data["n_users"], data["n_items"]
+    assert float((model.alpha_bar.cpu() - rp.ld4mrec_noise_schedule(model.steps, 0.001)).abs().max()) <= 1e-6
+    rng = np.random.default_rng(3)
+    b = 96
+    user = torch.from_numpy(rng.integers(0, nu, b)).to(model.device)
+    t = torch.from_numpy(rng.integers(0, 7, b)).to(model.device)     # 7 distinct steps: every step repeats in the batch
+    noise = torch.from_numpy(rng.standard_normal((b, ni)).astype(np.float32)).to(model.device)
+    # history rows == the dense slice of the train matrix the reference takes on the host
+    tr = data["label"] == 0
+    dense = np.zeros((nu, ni), dtype=np.float32)
+    dense[data["users"][tr], data["items"][tr]] = 1.0
+    x_in = model.history_rows(user)
+    assert np.array_equal(x_in.cpu().numpy(), dense[user.cpu().numpy()])
+    h0 = model.loss_history.clone()
+    h0 += torch.linspace(0, 1, model.steps, device=h0.device)          # a non-trivial starting history
+    model.loss_history.copy_(h0)
+    loss = model.calculate_loss((user,), t=t, noise=noise)
+    loss.backward()
+    p = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    rows = rp.ld4mrec_loss(p, dense[user.cpu().numpy()], t.cpu(), noise.cpu(), model.alpha_bar.cpu(),
+                           model.user_svd_emb[user].cpu(), model.user_mm_emb[user].cpu(), model.cnet_layers,
+                           model.smoothing_gamma)
+    assert abs(float(loss) - float(rows.mean())) <= 2e-5 * abs(float(rows.mean()))
+    want_h = rp.ld4mrec_loss_history(h0.cpu().numpy(), t.cpu().numpy(), rows.numpy())
+    assert float(np.abs(model.loss_history.cpu().numpy() - want_h).max()) <= 1e-5 * float(np.abs(want_h).max())
+    assert model.cnet.output_proj.weight.grad is not None and bool(torch.isfinite(model.cnet.output_proj.weight.grad).all())
+    # without fixed draws: steps come from the device-resident history (torch.multinomial), the loss is finite
+    assert bool(torch.isfinite(model.calculate_loss((user,))))
+
+
 def test_forward_cl_mm_multi_rhs_equals_per_view_chains(env):  # noqa: F811
     z, meta = load_golden("toy_diffmm")
     data = toy_arrays()

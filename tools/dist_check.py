@@ -60,7 +60,8 @@ def main():
     res = {"rank": rank, "world": world, "users_block": [sh.u0, sh.u1], "items_block": [sh.i0, sh.i1],
            "user_rows_rel_err": tol_u, "gathered_items_rel_err": tol_i, "topk_rows_identical": same_rows,
            "metric_sums_match": ok_m}
-    print(json.dumps(res), flush=True)
+    sys.stdout.flush()
+    os.write(1, (json.dumps(res) + "\n").encode())   # one write per rank: lines of different ranks never interleave
     sh.close()
     dist.barrier()
     dist.destroy_process_group()
