@@ -224,9 +224,16 @@ def run_gpu(args, workload, steps, warmup, main=True):
     full_loader = wl.valid
     sharded = None
     if world > 1:
-        from genmmrec_b200.dist import ShardedDiffMM, shard_eval_by_user_block, sharded_genrecv1
+        from genmmrec_b200.dist import (ColShardedDiffMM, ShardedDiffMM, col_shard_supported, shard_eval_by_user_block,
+                                        sharded_genrecv1)
         if model_name == "DiffMM":
-            sharded = ShardedDiffMM(model)
+            # GMR_DIST_MODE: cols (default where the world size allows it) = embedding columns sharded, SpMM layers local;
+            # rows = adjacency rows sharded, layer outputs all-gathered by peer stores
+            mode = os.environ.get("GMR_DIST_MODE", "cols")
+            if mode == "cols" and col_shard_supported(model.latdim, world):
+                sharded = ColShardedDiffMM(model)
+            else:
+                sharded = ShardedDiffMM(model)
         elif model_name == "GenRecV1":
             sharded = sharded_genrecv1(model)
         else:
@@ -415,8 +422,12 @@ def run_gpu(args, workload, steps, warmup, main=True):
                        "embedding_size": cfg["embedding_size"], "n_layers": cfg["n_layers"],
                        "score_precision": args.precision,
                        "launch": "CUDA graph replay of the whole step" if (use_graph and not graph_state["failed"]) else "eager launches",
-                       "parallelism": ("row-sharded propagation (each rank stores its row block into every peer's replica "
-                                       "over NVLink peer memory) + user-block sharded eval, x%d" % world)
+                       "parallelism": ((("column-sharded propagation (each rank owns %d of the %d embedding columns and runs every "
+                                         "SpMM over the whole graph locally; column slices exchanged by NVLink peer stores, "
+                                         "flag barriers in peer memory)" % (cfg["embedding_size"] // world, cfg["embedding_size"]))
+                                        if type(sharded).__name__ == "ColShardedDiffMM" else
+                                        "row-sharded propagation (each rank stores its row block into every peer's replica "
+                                        "over NVLink peer memory)") + " + user-block sharded eval, x%d" % world)
                        if world > 1 else "single GPU",
                        "l2": ("L2 flushed between timed steps (operands fit the %d MB L2)" % (l2_bytes >> 20)) if need_flush
                        else ("operands exceed the %d MB L2; no flush" % (l2_bytes >> 20))},

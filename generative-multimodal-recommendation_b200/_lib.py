@@ -54,6 +54,19 @@ SIGNATURES = {
     "gmr_bpr_scores_f32": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "gmr_bpr_scores_backward_f32": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _i64,
                                               _vp]),
+    "gmr_spmm_plan_enable_narrow": (C.c_int, [_vp, _vp, _vp]),
+    "gmr_spmm_narrow_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i32, _i32, _f32, _f32, _vp, _i64, _vp]),
+    "gmr_spmm_sell_create": (C.c_int, [C.POINTER(_vp), _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "gmr_spmm_sell_set_values": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "gmr_spmm_sell_destroy": (C.c_int, [_vp]),
+    "gmr_spmm_sell_bytes": (_i64, [_vp]),
+    "gmr_spmm_sell_f32": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i32, _i32, _f32, _f32, _vp, _i64, _vp]),
+    "gmr_cols_push_f32": (C.c_int, [_vp, _i64, _i64, _i32, _i64, _i64, _vp, _i32, _vp, _i64, _i64, _i64, _i32, _i64, _i64, _vp]),
+    "gmr_slabs_to_rows_f32": (C.c_int, [_vp, _i32, _i64, _i64, _i32, _vp, _i64, _vp]),
+    "gmr_rows_sumsq_f32": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp]),
+    "gmr_rows_axpby_ss_f32": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i32, _i64, _vp, _i64, _i64, _i32, _f32, _f32,
+                                        _f32, _f32, _vp]),
+    "gmr_peer_barrier": (C.c_int, [_vp, _i32, _i32, _vp, _vp]),
     "gmr_peer_alloc": (C.c_int, [C.POINTER(_vp), _i64]),
     "gmr_peer_free": (C.c_int, [_vp]),
     "gmr_peer_export": (C.c_int, [_vp, C.c_char_p]),

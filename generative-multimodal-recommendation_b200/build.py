@@ -14,7 +14,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB = os.path.join(PKG_DIR, "libgmr.so")
-SOURCES = ["api.cu", "spmm.cu", "spmm_flat.cu", "score_topk_simt.cu", "score_topk_tc.cu", "score_topk_screen.cu", "dense_proj.cu", "metrics.cu", "train_ops.cu"]
+SOURCES = ["api.cu", "spmm.cu", "spmm_flat.cu", "colshard.cu", "score_topk_simt.cu", "score_topk_tc.cu", "score_topk_screen.cu", "dense_proj.cu", "metrics.cu", "train_ops.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -169,6 +169,83 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// D = 64, 16-byte aligned rows: a half-warp per row (16 lanes x 128 bit), four rows in flight per half-warp -- the
+// one-row-per-warp kernels above keep a single 8-byte load per lane in flight and reach a fifth of the copy bandwidth
+// on this 128 MB pass, which every rank of a multi-GPU run repeats.
+__global__ void __launch_bounds__(256)
+    item_norms_d64_kernel(const float* __restrict__ E, int64_t lde, int32_t n_rows, uint32_t* __restrict__ gmax_bits,
+                          uint32_t* __restrict__ norm_bits, int32_t* __restrict__ ident)
+{
+    const int lane = threadIdx.x & 31, sub = lane & 15, half = lane >> 4;
+    const int64_t r0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 8 + half;
+    float4 x[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int64_t r = r0 + 2 * q;
+        x[q] = r < n_rows ? *reinterpret_cast<const float4*>(E + r * lde + 4 * sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float mm = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int64_t r = r0 + 2 * q;
+        float ss = fmaf(x[q].x, x[q].x, fmaf(x[q].y, x[q].y, fmaf(x[q].z, x[q].z, x[q].w * x[q].w)));
+        float m = fmaxf(fmaxf(fabsf(x[q].x), fabsf(x[q].y)), fmaxf(fabsf(x[q].z), fabsf(x[q].w)));
+#pragma unroll
+        for (int k = 8; k > 0; k >>= 1) {
+            ss += __shfl_xor_sync(0xffffffffu, ss, k);
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, k));
+        }
+        if (sub == 0 && r < n_rows) {
+            float nrm = sqrtf(ss) * 1.000001f;
+            if (!(nrm < INFINITY)) nrm = 3.0e38f;
+            norm_bits[r] = __float_as_uint(nrm);
+            ident[r] = (int32_t)r;
+            if (m > 0.f && m < INFINITY) mm = fmaxf(mm, m);
+        }
+    }
+    mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, 16));
+    if (lane == 0 && mm > 0.f && __float_as_uint(mm) > *reinterpret_cast<volatile uint32_t*>(gmax_bits))
+        atomicMax(gmax_bits, __float_as_uint(mm));
+}
+
+__global__ void __launch_bounds__(256)
+    prep_items_d64_kernel(const float* __restrict__ E, int64_t lde, int32_t n_rows, int32_t n_rows_pad,
+                          const uint32_t* __restrict__ gmax_bits, int32_t* __restrict__ perm, float* __restrict__ nb,
+                          __half* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31, sub = lane & 15, half = lane >> 4;
+    const int64_t p0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 8 + half;
+    const float s = pow2_scale_for(__uint_as_float(*gmax_bits));
+    int src[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int64_t p = p0 + 2 * q;
+        src[q] = p < n_rows ? perm[p] : -1;
+    }
+    float4 x[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        x[q] = src[q] >= 0 ? *reinterpret_cast<const float4*>(E + (int64_t)src[q] * lde + 4 * sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int64_t p = p0 + 2 * q;
+        if (p >= n_rows_pad) continue;
+        const __half2 lo = __floats2half2_rn(x[q].x * s, x[q].y * s), hi = __floats2half2_rn(x[q].z * s, x[q].w * s);
+        uint2 o;
+        o.x = *reinterpret_cast<const uint32_t*>(&lo);
+        o.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(out + p * 64 + 4 * sub) = o;
+        if (sub == 0) {
+            if (p >= n_rows) {
+                perm[p] = -1;
+                nb[p] = 0.f;
+            } else {
+                nb[p] *= s;
+            }
+        }
+    }
+}
+
 // users: per-row power-of-two scale; writes the row's error coefficients (eps(u, i) = ce * |e_i| + ab, scaled
 // units), its norm and the bias scale
 struct RowConst {
@@ -241,6 +318,60 @@ __global__ void __launch_bounds__(256)
         }
         rc.na = na;
         row_const[r] = rc;
+    }
+}
+
+// D = 64 form of prep_users_kernel (half-warp per row, four rows in flight per half-warp; see item_norms_d64_kernel)
+__global__ void __launch_bounds__(256)
+    prep_users_d64_kernel(const float* __restrict__ E, int64_t lde, const int64_t* __restrict__ rows, int32_t n_rows,
+                          int32_t n_rows_pad, const uint32_t* __restrict__ gmax_bits, const float* __restrict__ nb,
+                          const uint32_t* __restrict__ biasmax_bits, __half* __restrict__ out, RowConst* __restrict__ row_const)
+{
+    const int lane = threadIdx.x & 31, sub = lane & 15, half = lane >> 4;
+    const int64_t r0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 8 + half;
+    int64_t src[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int64_t r = r0 + 2 * q;
+        src[q] = r < n_rows ? (rows ? rows[r] : r) : -1;
+    }
+    float4 x[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        x[q] = src[q] >= 0 ? *reinterpret_cast<const float4*>(E + src[q] * lde + 4 * sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float nbmax = nb[0];  // sweep order is norm-descending
+    const float si = pow2_scale_for(__uint_as_float(*gmax_bits));
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int64_t r = r0 + 2 * q;
+        float m = fmaxf(fmaxf(fabsf(x[q].x), fabsf(x[q].y)), fmaxf(fabsf(x[q].z), fabsf(x[q].w)));
+#pragma unroll
+        for (int k = 8; k > 0; k >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, k));
+        const float su = pow2_scale_for(m);
+        const float x0 = x[q].x * su, x1 = x[q].y * su, x2 = x[q].z * su, x3 = x[q].w * su;
+        float ss = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, x3 * x3)));
+#pragma unroll
+        for (int k = 8; k > 0; k >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, k);
+        if (r >= n_rows_pad) continue;
+        const __half2 lo = __floats2half2_rn(x0, x1), hi = __floats2half2_rn(x2, x3);
+        uint2 o;
+        o.x = *reinterpret_cast<const uint32_t*>(&lo);
+        o.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(out + r * 64 + 4 * sub) = o;
+        if (sub == 0) {
+            float na = sqrtf(ss) * 1.000001f;
+            if (!(na < INFINITY)) na = INFINITY;
+            RowConst rc;
+            rc.sc = su * si;
+            rc.ce = kScreenErr * na;
+            rc.ab = 1e-6f * (na + nbmax);
+            if (biasmax_bits != nullptr) {
+                rc.ce += 2.4e-7f * na;
+                rc.ab += 2.4e-7f * rc.sc * __uint_as_float(*biasmax_bits);
+            }
+            rc.na = na;
+            row_const[r] = rc;
+        }
     }
 }
 
@@ -1118,17 +1249,28 @@ int score_topk_screen_launch(const float* Eu, int64_t lde_u, const int64_t* user
         absmax_kernel<<<grid, wpb * 32, 0, st>>>(bias, 1, I, 1, misc + 3);
         GMR_LAUNCH_CHECK();
     }
-    item_norms_kernel<<<(I + wpb - 1) / wpb, wpb * 32, 0, st>>>(Ei, lde_i, I, D, misc, nb_raw, ident);
+    const bool items_d64 = D == 64 && lde_i % 4 == 0 && (uintptr_t)Ei % 16 == 0;
+    if (items_d64)
+        item_norms_d64_kernel<<<(I + 8 * wpb - 1) / (8 * wpb), wpb * 32, 0, st>>>(Ei, lde_i, I, misc, nb_raw, ident);
+    else
+        item_norms_kernel<<<(I + wpb - 1) / wpb, wpb * 32, 0, st>>>(Ei, lde_i, I, D, misc, nb_raw, ident);
     GMR_LAUNCH_CHECK();
     {
         size_t tmp = (size_t)L.sort_tmp_bytes;
         GMR_CHECK_CUDA(cub::DeviceRadixSort::SortPairsDescending(ws + L.sort_tmp, tmp, nb_raw, (uint32_t*)nb, ident, perm, I,
                                                                  0, 32, st));
     }
-    prep_items_kernel<<<(L.i_pad + wpb - 1) / wpb, wpb * 32, 0, st>>>(Ei, lde_i, I, L.i_pad, D, misc, perm, nb, b_h);
+    if (items_d64)
+        prep_items_d64_kernel<<<(L.i_pad + 8 * wpb - 1) / (8 * wpb), wpb * 32, 0, st>>>(Ei, lde_i, I, L.i_pad, misc, perm, nb, b_h);
+    else
+        prep_items_kernel<<<(L.i_pad + wpb - 1) / wpb, wpb * 32, 0, st>>>(Ei, lde_i, I, L.i_pad, D, misc, perm, nb, b_h);
     GMR_LAUNCH_CHECK();
-    prep_users_kernel<<<(L.b_pad + wpb - 1) / wpb, wpb * 32, 0, st>>>(Eu, lde_u, users, B, L.b_pad, D, misc, nb,
-                                                                     bias ? misc + 3 : nullptr, a_h, row_const);
+    if (D == 64 && lde_u % 4 == 0 && (uintptr_t)Eu % 16 == 0)
+        prep_users_d64_kernel<<<(L.b_pad + 8 * wpb - 1) / (8 * wpb), wpb * 32, 0, st>>>(Eu, lde_u, users, B, L.b_pad, misc, nb,
+                                                                                       bias ? misc + 3 : nullptr, a_h, row_const);
+    else
+        prep_users_kernel<<<(L.b_pad + wpb - 1) / wpb, wpb * 32, 0, st>>>(Eu, lde_u, users, B, L.b_pad, D, misc, nb,
+                                                                         bias ? misc + 3 : nullptr, a_h, row_const);
     GMR_LAUNCH_CHECK();
 
     CUtensorMap map_a, map_b;

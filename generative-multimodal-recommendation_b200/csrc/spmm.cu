@@ -22,6 +22,8 @@
 #include <algorithm>
 #include <vector>
 
+#include <cub/cub.cuh>
+
 #include "common.cuh"
 
 struct gmr_spmm_plan {
@@ -36,6 +38,7 @@ struct gmr_spmm_plan {
     int32_t* d_vrow = nullptr;         // [n_vrows]  row id, or -1 - slot for a chunk of a split row
     int32_t* d_split_row = nullptr;    // [n_split_rows]
     int32_t* d_split_first = nullptr;  // [n_split_rows + 1] first slot of each split row
+    int32_t* d_order = nullptr;        // [n_vrows] virtual rows by descending length (narrow kernels; built on demand)
 };
 
 namespace gmr {
@@ -320,6 +323,76 @@ __global__ void __launch_bounds__(kWarps * 32)
     }
 }
 
+// Packed form for rows of at most 32 Vec (D <= 128 floats with float4): a CTA takes 256 / (8 DV) split rows at once, 8 DV
+// threads per row (sub-range w, column vc).  One CTA per split row left all but 8 DV of its 256 threads idle -- with tens
+// of thousands of split rows that cost 30-90 us per product (0.18 ms of the 13.7 ms single-GPU step, 15 % of a narrow
+// pass).  Same sub-ranges, same order of additions: same bits as spmm_reduce_kernel.
+template <typename Vec>
+__global__ void __launch_bounds__(kWarps * 32)
+    spmm_reduce_packed_kernel(const int32_t* __restrict__ split_row, const int32_t* __restrict__ split_first,
+                              const float* __restrict__ partial, float* __restrict__ Y, int64_t ldy, int32_t DV, int32_t n_split,
+                              int32_t rows_per_cta, float alpha, float beta)
+{
+    using Ops = VecOps<Vec>;
+    constexpr int VEC = sizeof(Vec) / 4;
+    extern __shared__ float4 red_smem[];  // [rows_per_cta][kWarps][DV] Vec
+    Vec* red = reinterpret_cast<Vec*>(red_smem);
+    const int T = kWarps * DV;
+    const int lr = threadIdx.x / T, t = threadIdx.x - lr * T;
+    const int w = t / DV, vc = t - w * DV;
+    const int s = blockIdx.x * rows_per_cta + lr;
+    const bool active = lr < rows_per_cta && s < n_split;
+    int row = 0;
+    if (active) {
+        row = split_row[s];
+        const int first = split_first[s], n = split_first[s + 1] - first;
+        const int per = (n + kWarps - 1) / kWarps;
+        const int lo = min(n, w * per), hi = min(n, lo + per);
+        const Vec* base = reinterpret_cast<const Vec*>(partial + (int64_t)first * ((int64_t)DV * VEC));
+        Vec a = Ops::zero();
+        for (int k = lo; k < hi; ++k) a = Ops::add(a, base[(int64_t)k * DV + vc]);
+        red[(lr * kWarps + w) * DV + vc] = a;
+    }
+    __syncthreads();
+    if (active && w == 0) {
+        Vec a = red[(lr * kWarps) * DV + vc];
+#pragma unroll
+        for (int w2 = 1; w2 < kWarps; ++w2) a = Ops::add(a, red[(lr * kWarps + w2) * DV + vc]);
+        Vec* y = reinterpret_cast<Vec*>(Y + (int64_t)row * ldy) + vc;
+        *y = (beta == 0.f) ? Ops::scale(alpha, a) : Ops::axpby(alpha, a, beta, *y);
+    }
+}
+
+// the split-row reduction of a product into Y (not the push form): packed when a row fits 32 threads per sub-range
+template <typename Vec>
+static int launch_reduce(const gmr_spmm_plan* plan, const float* partial, float* Y, int64_t ldy, int32_t DV, float alpha,
+                         float beta, cudaStream_t st)
+{
+    if (plan->n_split_rows == 0) return GMR_OK;
+    if (kWarps * DV <= kWarps * 32) {
+        const int rows_per_cta = (kWarps * 32) / (kWarps * DV);
+        const size_t smem = (size_t)rows_per_cta * kWarps * DV * sizeof(Vec);
+        const unsigned grid = (unsigned)((plan->n_split_rows + rows_per_cta - 1) / rows_per_cta);
+        spmm_reduce_packed_kernel<Vec><<<grid, kWarps * 32, smem, st>>>(plan->d_split_row, plan->d_split_first, partial, Y, ldy, DV,
+                                                                       (int32_t)plan->n_split_rows, rows_per_cta, alpha, beta);
+        GMR_LAUNCH_CHECK();
+        return GMR_OK;
+    }
+    const size_t smem = (size_t)kWarps * DV * sizeof(Vec);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(spmm_reduce_kernel<Vec, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("row width of %d vectors too large for the split-row reduction (%zu B shared)", DV, smem);
+            return GMR_ERR_UNSUPPORTED;
+        }
+    }
+    PushArgs push{nullptr, 0, 0};
+    spmm_reduce_kernel<Vec, false><<<(unsigned)plan->n_split_rows, kWarps * 32, smem, st>>>(plan->d_split_row, plan->d_split_first,
+                                                                                           partial, Y, ldy, DV, alpha, beta, push);
+    GMR_LAUNCH_CHECK();
+    return GMR_OK;
+}
+
 // Short-row variant (D = 64 floats, float4 lanes): one HALF-warp per virtual row, so a warp retires two rows per trip.
 // kNN modality graphs (10 neighbours per item) and the merged modal-mix graph (~5 nonzeros per row) spend the general
 // kernel's time on per-row overhead, not on gathers: a full warp per row stages 256 slots for 5 entries and leaves half
@@ -407,6 +480,279 @@ __global__ void __launch_bounds__(kWarps * 32, 3)
     }
 }
 
+
+// ---- narrow rows (column-sharded propagation: a rank owns D = 8 / 16 / 32 / 64 of the embedding columns) ------------
+// A row of D floats needs only D / 4 lanes, so a warp works on RPW = 32 / (D/4 * CHAINS) virtual rows at once.  The
+// per-column operation order is the wide kernels': CHAINS = 2 keeps one sequential fmaf chain over the even and one over
+// the odd nonzeros of the virtual row and adds them at the end (what spmm_vrow_kernel does for D <= 64 and the short-row
+// kernel for D = 64); CHAINS = 1 is the single chain of the 128-column pass.  A column slice of the product therefore
+// has the SAME BITS as the corresponding columns of the wide product, which is what lets dist.ColShardedDiffMM shard the
+// propagation by embedding column and still return the single-GPU result.  Virtual rows are taken in descending-length
+// order (plan->d_order) so that the RPW rows a warp walks together have (almost) equal lengths; the LPR lanes of a row
+// load LPR consecutive (col, val) pairs with one instruction and hand them round by shuffle.
+template <int DC4, int CHAINS, bool IDENT>
+__global__ void __launch_bounds__(kWarps * 32, 5)
+    spmm_narrow_kernel(const int32_t* __restrict__ vptr, const int32_t* __restrict__ vrow, const int32_t* __restrict__ order,
+                       const int32_t* __restrict__ col, const float* __restrict__ val, const float* __restrict__ X,
+                       int64_t ldx, float* __restrict__ Y, int64_t ldy, float* __restrict__ partial, int64_t n_vrows,
+                       float alpha, float beta)
+{
+    using Ops = VecOps<float4>;
+    constexpr unsigned kFull = 0xffffffffu;
+    constexpr int LPR = DC4 * CHAINS;   // lanes per virtual row
+    constexpr int RPW = 32 / LPR;       // virtual rows per warp
+    constexpr int U = 4;                // gathers in flight per lane
+    constexpr int PER = U * CHAINS;     // nonzeros of a row consumed per iteration
+    constexpr int NLOAD = (PER + LPR - 1) / LPR;
+    static_assert(LPR <= 32 && (PER % LPR == 0 || LPR % PER == 0), "lane layout");
+    const int lane = threadIdx.x & 31;
+    const int rs = lane / LPR, within = lane % LPR, chain = within / DC4, sub = within % DC4;
+    const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+    const float4* __restrict__ Xl = reinterpret_cast<const float4*>(X) + sub;
+    const int64_t ldv = ldx >> 2;
+    const int64_t n_groups = (n_vrows + RPW - 1) / RPW;
+    const int64_t n_warps_grid = (int64_t)gridDim.x * kWarps;
+    for (int64_t grp = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); grp < n_groups; grp += n_warps_grid) {
+        const int64_t idx = grp * RPW + rs;
+        const bool live = idx < n_vrows;
+        int b = 0, e = 0, dst = 0;
+        if (live) {
+            const int v = order[idx];
+            b = vptr[v];
+            e = vptr[v + 1];
+            dst = IDENT ? v : vrow[v];
+        }
+        const int n = e - b;
+        int nmax = n;
+#pragma unroll
+        for (int m = LPR; m < 32; m <<= 1) nmax = max(nmax, __shfl_xor_sync(kFull, nmax, m));
+        const bool to_y = live && (IDENT || dst >= 0);
+        float4* yp = reinterpret_cast<float4*>(Y + (int64_t)(to_y ? dst : 0) * ldy) + sub;
+        float4 yold = Ops::zero();
+        if (to_y && chain == 0 && beta != 0.f) yold = *yp;
+        float4 acc = Ops::zero();
+        for (int base = 0; base < nmax; base += PER) {
+            int c[NLOAD];
+            float w[NLOAD];
+#pragma unroll
+            for (int l = 0; l < NLOAD; ++l) {
+                const int p = base + l * LPR + within;
+                c[l] = 0;
+                w[l] = 0.f;
+                if (p < n && (NLOAD > 1 || within < PER)) {
+                    c[l] = ld_stream_s32(col + b + p, pol_stream);
+                    w[l] = ld_stream_f32(val + b + p, pol_stream);
+                }
+            }
+            float4 xv[U];
+            float ww[U];
+            bool ok[U];
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+                const int pos = q * CHAINS + chain;             // position inside this iteration
+                const int l = (q * CHAINS) / LPR;               // which index load holds it (compile time)
+                const int cj = __shfl_sync(kFull, c[l], pos % LPR, LPR);
+                ww[q] = __shfl_sync(kFull, w[l], pos % LPR, LPR);
+                ok[q] = base + pos < n;
+                xv[q] = ok[q] ? Ops::gather(Xl + (int64_t)cj * ldv, pol_keep) : Ops::zero();
+            }
+#pragma unroll
+            for (int q = 0; q < U; ++q)
+                if (ok[q]) Ops::fma(acc, ww[q], xv[q]);
+        }
+        if (CHAINS == 2) acc = Ops::xor_add(acc, DC4);   // even chain + odd chain
+        if (chain == 0) {
+            if (to_y)
+                *yp = (beta == 0.f) ? Ops::scale(alpha, acc) : Ops::axpby(alpha, acc, beta, yold);
+            else if (live)
+                reinterpret_cast<float4*>(partial + (int64_t)(-1 - dst) * (DC4 * 4))[sub] = acc;
+        }
+    }
+}
+
+
+// ---- sliced-ELL form of the narrow kernel ---------------------------------------------------------------------------
+// The gathers of a column shard are bound by the L1 request rate (~1 cache line per clock and SM, measured:
+// tools/gather_narrow_bench.cu -- a 32-byte row costs as much as a 64-byte one), so every request the CSR stream takes
+// is a gather lost: eight rows x 16-byte pieces of `col` and of `val` per warp load are 32 requests per 64 nonzeros, half
+// as many as the gathers themselves.  The SELL snapshot stores the (col, val) pairs of the RPW rows a warp walks together
+// (same descending-length order as above) interleaved per iteration: block `it` of a group holds entries
+// [it * 8, it * 8 + 8) of each of its rows, row after row (512 contiguous bytes per warp with eight rows), nothing on the
+// path chases a row pointer, and the next entries are fetched while the current gathers are in flight.  Same per-column
+// operation order, same bits.
+constexpr int kSellPer = 8;   // entries of a row per iteration
+
+struct SellView {
+    const uint32_t* goff;   // [n_groups + 1] first block of each group
+    const int2* meta;       // [n_groups * RPW] (dst, n) per row slot; n = 0 for padding slots
+    const uint2* cv;        // [n_blocks + 1][RPW][8] (col, val bits)
+    int64_t n_groups;
+};
+
+template <int DC4, int CHAINS, int MINB>
+__global__ void __launch_bounds__(kWarps * 32, MINB)
+    spmm_sell_kernel(SellView sv, const float* __restrict__ X, int64_t ldx, float* __restrict__ Y, int64_t ldy,
+                     float* __restrict__ partial, float alpha, float beta)
+{
+    using Ops = VecOps<float4>;
+    constexpr int LPR = DC4 * CHAINS;
+    constexpr int RPW = 32 / LPR;
+    constexpr int PER = kSellPer;
+    constexpr int QPB = 2 / CHAINS;   // quads (4 steps of one chain) per 8-entry block: 1 with two chains, 2 with one
+    const int lane = threadIdx.x & 31;
+    const int rs = lane / LPR, within = lane % LPR, chain = within / DC4, sub = within % DC4;
+    const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+    const float4* __restrict__ Xl = reinterpret_cast<const float4*>(X) + sub;
+    const int64_t ldv = ldx >> 2;
+    const int64_t n_warps_grid = (int64_t)gridDim.x * kWarps;
+    int64_t grp = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (grp >= sv.n_groups) return;
+    // A lane reads the four entries of its chain's next quad itself (two 128-bit loads; the DC4 lanes of a chain read the
+    // same addresses and the snapshot stores a block chain-major: [p0 p2 p4 p6 | p1 p3 p5 p7] with two chains), so no
+    // index ever crosses lanes: on this kernel a shuffle costs an LSU wavefront exactly like a gathered row does, and the
+    // data pipe's one wavefront per clock is the bound (ncu: l1tex data-pipe wavefronts 95 % of peak).
+    auto load_quad = [&](const uint2* p, uint4& e01, uint4& e23) {
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                     : "=r"(e01.x), "=r"(e01.y), "=r"(e01.z), "=r"(e01.w) : "l"(p), "l"(pol_stream));
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                     : "=r"(e23.x), "=r"(e23.y), "=r"(e23.z), "=r"(e23.w) : "l"(p + 2), "l"(pol_stream));
+    };
+    auto load_header = [&](int64_t g, int2& m, uint32_t& o, uint32_t& oe) {
+        m = make_int2(0x7fffffff, 0);
+        o = oe = 0;
+        if (g < sv.n_groups) {
+            m = sv.meta[g * RPW + rs];
+            o = sv.goff[g];
+            oe = sv.goff[g + 1];
+        }
+    };
+    // quad j of a group starting at block `o`: block o + j / QPB, entries [chain * 4 + (j % QPB) * 4, +4) of row slot rs
+    auto quad_ptr = [&](uint32_t o, int j) {
+        return sv.cv + ((int64_t)o + j / QPB) * (RPW * PER) + rs * PER + (CHAINS == 2 ? chain * 4 : (j % QPB) * 4);
+    };
+    int2 meta;
+    uint32_t off, off_end;
+    load_header(grp, meta, off, off_end);
+    uint4 c01, c23;
+    load_quad(quad_ptr(off, 0), c01, c23);
+    while (true) {
+        const int64_t gnext = grp + n_warps_grid;
+        const bool has_next = gnext < sv.n_groups;
+        int2 meta1;
+        uint32_t off1, off_end1;
+        load_header(gnext, meta1, off1, off_end1);   // the next group's header travels under this group's gathers
+        const int n = meta.y, dst = meta.x;
+        const bool live = dst != 0x7fffffff;
+        const bool to_y = live && dst >= 0;
+        float4* yp = reinterpret_cast<float4*>(Y + (int64_t)(to_y ? dst : 0) * ldy) + sub;
+        float4 yold = Ops::zero();
+        if (to_y && chain == 0 && beta != 0.f) yold = *yp;
+        float4 acc = Ops::zero();
+        const int nquad = (int)(off_end - off) * QPB;
+        for (int j = 0; j < nquad; ++j) {
+            // the next quad's entries (or the next group's first quad) load under this quad's gathers
+            uint4 n01, n23;
+            load_quad((j + 1 < nquad) ? quad_ptr(off, j + 1) : quad_ptr(off1, 0), n01, n23);
+            const int pos0 = (CHAINS == 2) ? (j * 8 + chain) : (j * 4);   // row position of step 0; steps advance by CHAINS
+            const uint32_t cc[4] = {c01.x, c01.z, c23.x, c23.z};
+            const uint32_t wb[4] = {c01.y, c01.w, c23.y, c23.w};
+            float4 xv[4];
+            bool ok[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                ok[q] = pos0 + q * CHAINS < n;
+                xv[q] = ok[q] ? Ops::gather(Xl + (int64_t)cc[q] * ldv, pol_keep) : Ops::zero();
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (ok[q]) Ops::fma(acc, __uint_as_float(wb[q]), xv[q]);
+            c01 = n01;
+            c23 = n23;
+        }
+        if (nquad == 0) load_quad(quad_ptr(off1, 0), c01, c23);   // an all-empty group: its successor's first quad
+        if (CHAINS == 2) acc = Ops::xor_add(acc, DC4);
+        if (chain == 0) {
+            if (to_y)
+                *yp = (beta == 0.f) ? Ops::scale(alpha, acc) : Ops::axpby(alpha, acc, beta, yold);
+            else if (live)
+                reinterpret_cast<float4*>(partial + (int64_t)(-1 - dst) * (DC4 * 4))[sub] = acc;
+        }
+        if (!has_next) break;
+        grp = gnext;
+        meta = meta1; off = off1; off_end = off_end1;
+    }
+}
+
+// builders of the SELL snapshot
+__global__ void sell_group_iters_kernel(const int32_t* __restrict__ vptr, const int32_t* __restrict__ order, int64_t n_vrows,
+                                        int rpw, int64_t n_groups, uint32_t* __restrict__ iters)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const int v = order[g * rpw];   // longest row of the group (descending order)
+    const int n = vptr[v + 1] - vptr[v];
+    iters[g] = (uint32_t)((n + kSellPer - 1) / kSellPer);
+}
+
+// one warp per row slot: meta + the row's entries into its group's blocks
+template <bool IDENT>
+__global__ void __launch_bounds__(256)
+    sell_fill_kernel(const int32_t* __restrict__ vptr, const int32_t* __restrict__ vrow, const int32_t* __restrict__ order,
+                     const int32_t* __restrict__ col, const float* __restrict__ val, int64_t n_vrows, int rpw, int chains,
+                     int64_t n_slots, const uint32_t* __restrict__ goff, int2* __restrict__ meta, uint2* __restrict__ cv)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n_slots) return;
+    if (i >= n_vrows) {
+        if (lane == 0) meta[i] = make_int2(0x7fffffff, 0);   // padding slot of the last group
+        return;
+    }
+    const int v = order[i];
+    const int b = vptr[v], n = vptr[v + 1] - b;
+    if (lane == 0) meta[i] = make_int2(IDENT ? v : vrow[v], n);
+    const int64_t g = i / rpw;
+    const int rs = (int)(i - g * rpw);
+    uint2* base = cv + (int64_t)goff[g] * (rpw * kSellPer) + rs * kSellPer;
+    for (int p = lane; p < n; p += 32) {
+        const int k = p % kSellPer;
+        const int slot = (chains == 2) ? ((k & 1) * 4 + (k >> 1)) : k;   // two chains: even entries first, then the odd ones
+        base[(int64_t)(p / kSellPer) * (rpw * kSellPer) + slot] = make_uint2((uint32_t)col[b + p], __float_as_uint(val[b + p]));
+    }
+}
+
+// iota for the order sort
+__global__ void iota_len_kernel(const int32_t* __restrict__ vptr, int64_t n, uint32_t* __restrict__ len, int32_t* __restrict__ id)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        len[i] = (uint32_t)(vptr[i + 1] - vptr[i]);
+        id[i] = (int32_t)i;
+    }
+}
+
+template <int DC4, int CHAINS>
+static int launch_narrow(const gmr_spmm_plan* plan, const int32_t* rowptr, const int32_t* col, const float* val,
+                         const float* X, int64_t ldx, float* Y, int64_t ldy, float* partial, float alpha, float beta,
+                         cudaStream_t st)
+{
+    constexpr int RPW = 32 / (DC4 * CHAINS);
+    const int64_t nv = plan->n_vrows;
+    if (nv == 0) return GMR_OK;
+    const int64_t groups = (nv + RPW - 1) / RPW;
+    const int64_t want = (groups + kWarps - 1) / kWarps;
+    const int64_t cap = (int64_t)sm_count() * 5;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    if (plan->d_vptr == nullptr)
+        spmm_narrow_kernel<DC4, CHAINS, true><<<grid, kWarps * 32, 0, st>>>(rowptr, nullptr, plan->d_order, col, val, X, ldx, Y,
+                                                                           ldy, partial, nv, alpha, beta);
+    else
+        spmm_narrow_kernel<DC4, CHAINS, false><<<grid, kWarps * 32, 0, st>>>(plan->d_vptr, plan->d_vrow, plan->d_order, col,
+                                                                            val, X, ldx, Y, ldy, partial, nv, alpha, beta);
+    GMR_LAUNCH_CHECK();
+    return GMR_OK;
+}
+
 // GMR_SPMM_SHORT: unset = pick by mean virtual-row length, 0 = never, 1 = whenever the shape allows.  Read on every call
 // (a getenv is noise next to a launch) so the tests can run both kernels in one process.
 static int spmm_short_mode()
@@ -486,6 +832,7 @@ static int dispatch(const gmr_spmm_plan* plan, const int32_t* rowptr, const int3
     else
         rc = launch_vrow<Vec, 32, 4, PUSH>(plan, rowptr, col, val, X, ldx, Y, ldy, partial, DV, alpha, beta, push, st);
     if (rc != GMR_OK) return rc;
+    if (!PUSH) return launch_reduce<Vec>(plan, partial, Y, ldy, DV, alpha, beta, st);
     if (plan->n_split_rows > 0) {
         const size_t smem = (size_t)kWarps * DV * sizeof(Vec);
         if (smem > 48 * 1024) {
@@ -576,7 +923,9 @@ __global__ void __launch_bounds__(256)
         if (ok) zv = *reinterpret_cast<const float4*>(z + r * ldz + 4 * sub);
         float ss = fmaf(zv.x, zv.x, fmaf(zv.y, zv.y, fmaf(zv.z, zv.z, zv.w * zv.w)));
 #pragma unroll
-        for (int m = 8; m > 0; m >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, m);   // within the 16-lane half
+        // neighbours first (1, 2, 4, 8): every aligned block of 2 / 4 / 8 lanes is a subtree, so a rank that owns a contiguous
+        // block of columns can form its part of the sum and the parts combine to the same bits (gmr_rows_sumsq_f32)
+        for (int m = 1; m < 16; m <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, m);   // within the 16-lane half
         inv = c / fmaxf(sqrtf(ss), eps);
     }
     if (!ok) return;
@@ -744,6 +1093,7 @@ extern "C" int gmr_spmm_plan_destroy(gmr_spmm_plan_t* p)
     cudaFree(p->d_vrow);
     cudaFree(p->d_split_row);
     cudaFree(p->d_split_first);
+    cudaFree(p->d_order);
     delete p;
     return GMR_OK;
 }
@@ -782,6 +1132,232 @@ extern "C" int gmr_spmm_csr_f32_push(const gmr_spmm_plan_t* plan, const int32_t*
     gmr::PushArgs push{y_peers, n_peers, row_offset};
     return gmr::spmm_common(plan, rowptr, col, val, X, ldx, nullptr, ldy, D, alpha, 0.f, push, true, workspace,
                             workspace_bytes, stream);
+}
+
+
+extern "C" int gmr_spmm_plan_enable_narrow(gmr_spmm_plan_t* p, const int32_t* rowptr, void* stream)
+{
+    GMR_REQUIRE(p != nullptr, "gmr_spmm_plan_enable_narrow: null plan");
+    if (p->d_order != nullptr || p->n_vrows == 0) return GMR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = p->n_vrows;
+    const int32_t* vptr = p->d_vptr ? p->d_vptr : rowptr;
+    GMR_REQUIRE(vptr != nullptr, "gmr_spmm_plan_enable_narrow: null rowptr");
+    uint32_t *len = nullptr, *len_out = nullptr;
+    int32_t *id = nullptr, *order = nullptr;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    cudaError_t e = cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, len, len_out, id, order, (int)n, 0, 32, st);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&len, sizeof(uint32_t) * n);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&len_out, sizeof(uint32_t) * n);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&id, sizeof(int32_t) * n);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&order, sizeof(int32_t) * n);
+    if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1);
+    if (e == cudaSuccess) {
+        gmr::iota_len_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(vptr, n, len, id);
+        e = cudaGetLastError();
+    }
+    // stable: virtual rows of equal length keep their row order
+    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, len, len_out, id, order, (int)n, 0, 32, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(len);
+    cudaFree(len_out);
+    cudaFree(id);
+    cudaFree(tmp);
+    if (e != cudaSuccess) {
+        cudaFree(order);
+        gmr::set_error("gmr_spmm_plan_enable_narrow: %s", cudaGetErrorString(e));
+        return GMR_ERR_CUDA;
+    }
+    p->d_order = order;
+    return GMR_OK;
+}
+
+extern "C" int gmr_spmm_narrow_f32(const gmr_spmm_plan_t* plan, const int32_t* rowptr, const int32_t* col, const float* val,
+                                   const float* X, int64_t ldx, float* Y, int64_t ldy, int32_t D, int32_t chains, float alpha,
+                                   float beta, void* workspace, int64_t workspace_bytes, void* stream)
+{
+    GMR_REQUIRE(plan != nullptr, "gmr_spmm_narrow_f32: plan is null");
+    GMR_REQUIRE((D == 8 || D == 16 || D == 32 || D == 64) && (chains == 1 || chains == 2),
+                "gmr_spmm_narrow_f32: D must be 8, 16, 32 or 64 and chains 1 or 2 (got D=%d chains=%d)", D, chains);
+    GMR_REQUIRE(!(D == 64 && chains == 2), "gmr_spmm_narrow_f32: D=64 with two chains is the wide kernel (gmr_spmm_csr_f32)");
+    GMR_REQUIRE(ldx >= D && ldy >= D && ldx % 4 == 0 && ldy % 4 == 0, "gmr_spmm_narrow_f32: bad leading dimensions (%lld, %lld)",
+                (long long)ldx, (long long)ldy);
+    if (plan->n_rows == 0) return GMR_OK;
+    GMR_REQUIRE(rowptr && X && Y && (uintptr_t)X % 16 == 0 && (uintptr_t)Y % 16 == 0, "gmr_spmm_narrow_f32: null or unaligned operand");
+    GMR_REQUIRE(plan->nnz == 0 || (col && val), "gmr_spmm_narrow_f32: null col/val with nnz > 0");
+    GMR_REQUIRE(plan->d_order != nullptr || plan->n_vrows == 0, "gmr_spmm_narrow_f32: call gmr_spmm_plan_enable_narrow first");
+    const int64_t need = gmr_spmm_workspace_bytes(plan, D);
+    if (need > 0 && (workspace == nullptr || workspace_bytes < need)) {
+        gmr::set_error("gmr_spmm_narrow_f32: workspace of %lld bytes required, %lld given", (long long)need, (long long)workspace_bytes);
+        return GMR_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    float* partial = (float*)workspace;
+    int rc = GMR_ERR_INVALID;
+#define GMR_NARROW(DC4, CH) \
+    rc = gmr::launch_narrow<DC4, CH>(plan, rowptr, col, val, X, ldx, Y, ldy, partial, alpha, beta, st)
+    if (D == 8 && chains == 2) GMR_NARROW(2, 2);
+    else if (D == 8) GMR_NARROW(2, 1);
+    else if (D == 16 && chains == 2) GMR_NARROW(4, 2);
+    else if (D == 16) GMR_NARROW(4, 1);
+    else if (D == 32 && chains == 2) GMR_NARROW(8, 2);
+    else if (D == 32) GMR_NARROW(8, 1);
+    else GMR_NARROW(16, 1);
+#undef GMR_NARROW
+    if (rc != GMR_OK) return rc;
+    return gmr::launch_reduce<float4>(plan, partial, Y, ldy, D / 4, alpha, beta, st);
+}
+
+struct gmr_spmm_sell {
+    const gmr_spmm_plan* base = nullptr;
+    int32_t rpw = 0, chains = 0;
+    int64_t n_groups = 0, n_blocks = 0;
+    uint32_t* d_goff = nullptr;
+    int2* d_meta = nullptr;
+    uint2* d_cv = nullptr;
+};
+
+static int sell_fill(gmr_spmm_sell* s, const int32_t* rowptr, const int32_t* col, const float* val, cudaStream_t st)
+{
+    const gmr_spmm_plan* p = s->base;
+    const int64_t n_slots = s->n_groups * s->rpw;
+    GMR_CHECK_CUDA(cudaMemsetAsync(s->d_cv, 0, sizeof(uint2) * (size_t)(s->n_blocks + 1) * s->rpw * gmr::kSellPer, st));
+    const unsigned grid = (unsigned)((n_slots * 32 + 255) / 256);
+    if (p->d_vptr == nullptr)
+        gmr::sell_fill_kernel<true><<<grid, 256, 0, st>>>(rowptr, nullptr, p->d_order, col, val, p->n_vrows, s->rpw, s->chains, n_slots,
+                                                         s->d_goff, s->d_meta, s->d_cv);
+    else
+        gmr::sell_fill_kernel<false><<<grid, 256, 0, st>>>(p->d_vptr, p->d_vrow, p->d_order, col, val, p->n_vrows, s->rpw, s->chains,
+                                                          n_slots, s->d_goff, s->d_meta, s->d_cv);
+    GMR_LAUNCH_CHECK();
+    return GMR_OK;
+}
+
+extern "C" int gmr_spmm_sell_destroy(gmr_spmm_sell_t* s)
+{
+    if (s == nullptr) return GMR_OK;
+    cudaFree(s->d_goff);
+    cudaFree(s->d_meta);
+    cudaFree(s->d_cv);
+    delete s;
+    return GMR_OK;
+}
+
+extern "C" int gmr_spmm_sell_create(gmr_spmm_sell_t** out, gmr_spmm_plan_t* plan, const int32_t* rowptr, const int32_t* col,
+                                    const float* val, int32_t D, int32_t chains, void* stream)
+{
+    GMR_REQUIRE(out != nullptr && plan != nullptr, "gmr_spmm_sell_create: null argument");
+    *out = nullptr;
+    GMR_REQUIRE((D == 8 || D == 16 || D == 32 || D == 64) && (chains == 1 || chains == 2) && !(D == 64 && chains == 2),
+                "gmr_spmm_sell_create: D must be 8, 16, 32 (chains 1 or 2) or 64 (chains 1); got D=%d chains=%d", D, chains);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = gmr_spmm_plan_enable_narrow(plan, rowptr, stream);
+    if (rc != GMR_OK) return rc;
+    auto* s = new gmr_spmm_sell();
+    s->base = plan;
+    s->rpw = 32 / ((D / 4) * chains);
+    s->chains = chains;
+    s->n_groups = (plan->n_vrows + s->rpw - 1) / s->rpw;
+    if (s->n_groups == 0) {
+        *out = s;
+        return GMR_OK;
+    }
+    const int32_t* vptr = plan->d_vptr ? plan->d_vptr : rowptr;
+    uint32_t* iters = nullptr;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    const int ng = (int)s->n_groups;
+    cudaError_t e = cudaMalloc((void**)&iters, sizeof(uint32_t) * (ng + 1));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_goff, sizeof(uint32_t) * (ng + 1));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_meta, sizeof(int2) * (size_t)ng * s->rpw);
+    if (e == cudaSuccess) e = cudaMemsetAsync(iters, 0, sizeof(uint32_t) * (ng + 1), st);
+    if (e == cudaSuccess) {
+        gmr::sell_group_iters_kernel<<<(unsigned)((ng + 255) / 256), 256, 0, st>>>(vptr, plan->d_order, plan->n_vrows, s->rpw, ng, iters);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, iters, s->d_goff, ng + 1, st);
+    if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1);
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, iters, s->d_goff, ng + 1, st);
+    uint32_t total = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&total, s->d_goff + ng, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(iters);
+    cudaFree(tmp);
+    s->n_blocks = total;
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_cv, sizeof(uint2) * (size_t)(s->n_blocks + 1) * s->rpw * gmr::kSellPer);
+    if (e != cudaSuccess) {
+        gmr::set_error("gmr_spmm_sell_create: %s", cudaGetErrorString(e));
+        gmr_spmm_sell_destroy(s);
+        return GMR_ERR_CUDA;
+    }
+    rc = sell_fill(s, rowptr, col, val, st);
+    if (rc != GMR_OK) {
+        gmr_spmm_sell_destroy(s);
+        return rc;
+    }
+    *out = s;
+    return GMR_OK;
+}
+
+extern "C" int gmr_spmm_sell_set_values(gmr_spmm_sell_t* s, const int32_t* rowptr, const int32_t* col, const float* val, void* stream)
+{
+    GMR_REQUIRE(s != nullptr, "gmr_spmm_sell_set_values: null snapshot");
+    if (s->n_groups == 0) return GMR_OK;
+    return sell_fill(s, rowptr, col, val, (cudaStream_t)stream);
+}
+
+extern "C" int64_t gmr_spmm_sell_bytes(const gmr_spmm_sell_t* s)
+{
+    if (s == nullptr) return 0;
+    return (int64_t)sizeof(uint2) * (s->n_blocks + 1) * s->rpw * gmr::kSellPer + (int64_t)sizeof(int2) * s->n_groups * s->rpw +
+           (int64_t)sizeof(uint32_t) * (s->n_groups + 1);
+}
+
+extern "C" int gmr_spmm_sell_f32(const gmr_spmm_sell_t* s, const float* X, int64_t ldx, float* Y, int64_t ldy, int32_t D,
+                                 int32_t chains, float alpha, float beta, void* workspace, int64_t workspace_bytes, void* stream)
+{
+    GMR_REQUIRE(s != nullptr, "gmr_spmm_sell_f32: null snapshot");
+    GMR_REQUIRE((D == 8 || D == 16 || D == 32 || D == 64) && (chains == 1 || chains == 2) && !(D == 64 && chains == 2) &&
+                    32 / ((D / 4) * chains) == s->rpw && chains == s->chains,
+                "gmr_spmm_sell_f32: D=%d chains=%d does not match the snapshot (%d rows per warp, %d chains)", D, chains, s->rpw,
+                s->chains);
+    GMR_REQUIRE(ldx >= D && ldy >= D && ldx % 4 == 0 && ldy % 4 == 0, "gmr_spmm_sell_f32: bad leading dimensions (%lld, %lld)",
+                (long long)ldx, (long long)ldy);
+    const gmr_spmm_plan* plan = s->base;
+    if (plan->n_rows == 0 || s->n_groups == 0) return GMR_OK;
+    GMR_REQUIRE(X && Y && (uintptr_t)X % 16 == 0 && (uintptr_t)Y % 16 == 0, "gmr_spmm_sell_f32: null or unaligned operand");
+    const int64_t need = gmr_spmm_workspace_bytes(plan, D);
+    if (need > 0 && (workspace == nullptr || workspace_bytes < need)) {
+        gmr::set_error("gmr_spmm_sell_f32: workspace of %lld bytes required, %lld given", (long long)need, (long long)workspace_bytes);
+        return GMR_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    float* partial = (float*)workspace;
+    gmr::SellView sv{s->d_goff, s->d_meta, s->d_cv, s->n_groups};
+    const int64_t want = (s->n_groups + gmr::kWarps - 1) / gmr::kWarps;
+    // resident CTAs per SM: 3 (no spills; measured 3-5 % faster) or 4 (64 registers, a few spilled words); GMR_SELL_MINB picks
+    const char* mb = getenv("GMR_SELL_MINB");
+    const int minb = (mb && atoi(mb) == 4) ? 4 : 3;
+    const int64_t cap = (int64_t)gmr::sm_count() * minb;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+#define GMR_SELL(DC4, CH)                                                                                                   \
+    do {                                                                                                                    \
+        if (minb == 3)                                                                                                      \
+            gmr::spmm_sell_kernel<DC4, CH, 3><<<grid, gmr::kWarps * 32, 0, st>>>(sv, X, ldx, Y, ldy, partial, alpha, beta);  \
+        else                                                                                                                \
+            gmr::spmm_sell_kernel<DC4, CH, 4><<<grid, gmr::kWarps * 32, 0, st>>>(sv, X, ldx, Y, ldy, partial, alpha, beta);  \
+    } while (0)
+    if (D == 8 && chains == 2) GMR_SELL(2, 2);
+    else if (D == 8) GMR_SELL(2, 1);
+    else if (D == 16 && chains == 2) GMR_SELL(4, 2);
+    else if (D == 16) GMR_SELL(4, 1);
+    else if (D == 32 && chains == 2) GMR_SELL(8, 2);
+    else if (D == 32) GMR_SELL(8, 1);
+    else GMR_SELL(16, 1);
+#undef GMR_SELL
+    GMR_LAUNCH_CHECK();
+    return gmr::launch_reduce<float4>(plan, partial, Y, ldy, D / 4, alpha, beta, st);
 }
 
 extern "C" int gmr_rows_axpby_norm_f32(const float* x, int64_t ldx, const float* y, int64_t ldy, const float* z,

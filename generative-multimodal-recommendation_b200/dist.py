@@ -351,6 +351,229 @@ class ShardedDiffMM(object):
         return out_u, self.items_all.tensor
 
 
+class _LocalReplicas(object):
+    """``world`` same-shaped buffers in ONE process standing in for the replicas of a PeerBuffer (single-GPU emulation of
+    the ranks in the tests: every 'rank' sees the same pointer table)."""
+
+    def __init__(self, rows, cols, device, world):
+        self.tensors = [torch.zeros((int(rows), int(cols)), dtype=torch.float32, device=device) for _ in range(world)]
+        self.ptr_table = torch.tensor([t.data_ptr() for t in self.tensors], dtype=torch.int64, device=device)
+
+    def view(self, rank):
+        class V(object):
+            pass
+        v = V()
+        v.tensor, v.ptr_table, v.close = self.tensors[rank], self.ptr_table, (lambda: None)
+        return v
+
+
+class PeerBarrier(object):
+    """Stream-ordered cross-rank barrier through flags in peer memory (``gmr_peer_barrier``): one 32-thread kernel per
+    rank instead of a 1-element NCCL all-reduce.  ``check()`` (host, synchronising) raises if a peer ever failed to arrive."""
+
+    def __init__(self, device, group=None, replicas=None, rank=None, world=None):
+        if replicas is None:
+            self.flags = PeerBuffer(1, 64, device, group)
+            self.rank, self.world = self.flags.rank, self.flags.world
+        else:
+            self.flags, self.rank, self.world = replicas, rank, world
+        self.state = torch.zeros(2, dtype=torch.int32, device=device)
+        self.device = torch.device(device)
+
+    def __call__(self):
+        if self.world <= 1:
+            return
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.gmr_peer_barrier(C.c_void_p(self.flags.ptr_table.data_ptr()), self.rank, self.world,
+                                            ops._ptr(self.state), ops._stream()), "gmr_peer_barrier")
+        ops.LAUNCHES += 1
+
+    def check(self):
+        n = int(self.state[1].item())
+        if n:
+            raise RuntimeError("gmr_peer_barrier: %d wait(s) timed out -- a peer rank never arrived" % n)
+
+    def close(self):
+        self.flags.close()
+
+
+def col_shard_supported(d, world):
+    """Column sharding needs a power-of-two world whose column share is 8, 16 or 32 floats."""
+    return world >= 2 and (world & (world - 1)) == 0 and d % world == 0 and (d // world) in (8, 16, 32)
+
+
+class ColShardedDiffMM(object):
+    """COLUMN-sharded ``forward_MM`` of a DiffMM replica: rank g owns columns [g dc, (g + 1) dc) of every embedding row.
+
+    ``A X`` is column-separable, so every SpMM of the regrouped dataflow (``DiffMM._forward_mm_fused``) runs locally over
+    the WHOLE graph on a [N, dc] operand that fits the L2 -- no all-gather of layer outputs (the row-sharded form moves
+    ~0.9 GB per rank and step at the 1M x 500k shape and loses the gather reuse of the single-GPU pass).  What is
+    exchanged, by peer stores (``gmr_cols_push_f32``) behind three barriers per step:
+
+        P0  projections of the item block (row-sharded: the dense features stay where they are) -> [Z | Z + I0] of the
+            block -> column slices to their owners (all-to-all, 2 x 4 dc bytes per item and peer); meanwhile
+            e0_c = [U0; I0][:, cols], modal_c = lambda (w0 A_v + w1 A_t) e0_c
+        P1  [R_hat Z | modal_u]_c += R_hat Xi_c (ONE 2dc-wide pass), xu_c = U0_c + R_hat Z, modal_i,c += R_hat' xu_c,
+            L_c = A modal_c; this rank's part of |modal|^2 per row -> every rank (4 bytes per row and peer)
+        P2  E_c = modal_c + L_c + ris_lambda modal_c / |modal|  (parts added as the single-GPU kernel's reduction tree);
+            item columns -> every rank's item table, user columns -> the rank that scores those users
+
+    The narrow SpMM keeps the wide kernels' per-column operation order and the norm parts combine like the 64-column
+    row kernel's butterfly, so user block and item table equal the single-GPU result bit for bit."""
+
+    def __init__(self, model, group=None, _emulate=None):
+        import torch.distributed as dist
+
+        self.model = m = model
+        self.group = group
+        self.dev = m.device
+        nu, ni, d = m.n_users, m.n_items, m.latdim
+        if _emulate is None:
+            self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+            self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        else:
+            self.rank, self.world = _emulate["rank"], _emulate["world"]
+        W, g = self.world, self.rank
+        if not col_shard_supported(d, W):
+            raise ValueError("column sharding needs a power-of-two world with 8, 16 or 32 columns per rank (d=%d, world=%d)" % (d, W))
+        self.dc = dc = d // W
+        self.c0 = g * dc
+        self.ub, self.ib = block_bounds(nu, W), block_bounds(ni, W)
+        self.u0, self.u1, self.i0, self.i1 = self.ub[g], self.ub[g + 1], self.ib[g], self.ib[g + 1]
+        n = nu + ni
+        self.n_pad = (n + 3) // 4 * 4
+        max_ub = max(self.ub[k + 1] - self.ub[k] for k in range(W))
+        self.max_ub = max_ub
+        # items_slab / users_slab: W column slabs [rows, dc], slab g written contiguously by rank g
+        shapes = {"xi_c": (ni, 2 * dc), "ss_all": (W * self.n_pad // 4, 4), "items_slab": (W * ni, dc), "users_slab": (W * max_ub, dc)}
+        if _emulate is None:
+            self.peer = {k: PeerBuffer(r, c, self.dev, group) for k, (r, c) in shapes.items()}
+            self.barrier = PeerBarrier(self.dev, group) if os.environ.get("GMR_PEER_BARRIER", "1") == "1" else None
+        else:
+            self.peer = {k: _emulate["replicas"][k].view(g) for k in shapes}
+            self.barrier = None
+        self._shapes = shapes
+        self.token = torch.zeros(1, device=self.dev)
+        mk = lambda r, c: torch.empty((r, c), dtype=torch.float32, device=self.dev)
+        self.buf = {"xi_local": mk(self.i1 - self.i0, 2 * d), "e0_c": mk(n, dc), "yu_c": mk(nu, 2 * dc), "modal_c": mk(n, dc), "xu_c": mk(nu, dc),
+                    "last_c": mk(n, dc), "emb_c": mk(n, dc), "ss": torch.zeros(self.n_pad, dtype=torch.float32, device=self.dev),
+                    "items_all": mk(ni, d), "users_blk": mk(max_ub, d)}
+        self.self_table = {k: torch.tensor([v.data_ptr()], dtype=torch.int64, device=self.dev) for k, v in self.buf.items()}
+        self.ub_dev = torch.tensor(self.ub, dtype=torch.int64, device=self.dev)
+
+    @classmethod
+    def emulate(cls, model, world):
+        """``world`` instances in one process over shared local replicas (tests): run with ``emulated_eval_factors``."""
+        nu, ni, d = model.n_users, model.n_items, model.latdim
+        dc = d // world
+        n_pad = (nu + ni + 3) // 4 * 4
+        ub = block_bounds(nu, world)
+        max_ub = max(ub[k + 1] - ub[k] for k in range(world))
+        shapes = {"xi_c": (ni, 2 * dc), "ss_all": (world * n_pad // 4, 4), "items_slab": (world * ni, dc), "users_slab": (world * max_ub, dc)}
+        reps = {k: _LocalReplicas(r, c, model.device, world) for k, (r, c) in shapes.items()}
+        return [cls(model, _emulate={"rank": g, "world": world, "replicas": reps}) for g in range(world)]
+
+    @staticmethod
+    def emulated_eval_factors(ranks):
+        """Run the three phases of every emulated rank in lockstep; returns [(user block, item table)] per rank."""
+        for fn in ("_p0", "_p1", "_p2", "_p3"):
+            for r in ranks:
+                getattr(r, fn)()
+        return [r._result() for r in ranks]
+
+    def _sync(self):
+        if self.barrier is not None:
+            self.barrier()
+        else:
+            stream_barrier(self.token)
+
+    # ---- phases ------------------------------------------------------------------------------------------------
+    def _p0(self):
+        m = self.model
+        nu, d, dc, W = m.n_users, m.latdim, self.dc, self.world
+        i0, i1 = self.i0, self.i1
+        w0, w1 = m._modal_weights_host()
+        e0 = m._packed_e0()
+        pv = m._project(m.v_feat[i0:i1], m.image_trans.detach())
+        pt = m._project(m.t_feat[i0:i1], m.text_trans.detach())
+        xi_local = ops.rows_normalize_mix(pv, pt, w0, w1, y=e0[nu + i0:nu + i1], slope=m.leakyrelu.negative_slope,
+                                          out=self.buf["xi_local"])
+        xi_tab = self.peer["xi_c"].ptr_table
+        # all-to-all of column slices: peer h receives [Z[:, cols_h] | (Z + I0)[:, cols_h]] of this item block
+        # (both halves in one launch: a destination row is the two slices side by side, so the remote stores are contiguous)
+        ops.cols_push(xi_local, dc, xi_tab, W, 2 * dc, src_col0=0, src_col_step=dc, dst_row_offset=i0, dst_col0=0, tag="xi",
+                      n_seg=2, src_seg_step=d, dst_seg_step=dc)
+        # local work under the transfer: this rank's columns of [U0; I0], and the modality-graph term as the seed of modal_c
+        e0_c = self.buf["e0_c"]
+        ops.cols_push(e0, dc, self.self_table["e0_c"], 1, dc, src_col0=self.c0, tag="e0_local")
+        mix = m._modal_mix_graph(m.image_UI_matrix, m.text_UI_matrix, w0, w1)
+        ops.spmm_narrow(mix, e0_c, chains=2, out=self.buf["modal_c"])
+
+    def _p1(self):
+        m = self.model
+        nu, dc = m.n_users, self.dc
+        adj = m.norm_adj
+        yu, modal, e0_c = self.buf["yu_c"], self.buf["modal_c"], self.buf["e0_c"]
+        ops.spmm_narrow(adj.ui, self.peer["xi_c"].tensor, chains=1, out=yu)                    # [R_hat Z | R_hat (Z + I0)] (cols)
+        xu = ops.rows_axpby_ss(e0_c[:nu], yu[:, :dc], a=1.0, b=1.0, out=self.buf["xu_c"])      # U0 + R_hat Z
+        ops.rows_axpby_ss(modal[:nu], yu[:, dc:], a=1.0, b=1.0, out=modal[:nu])                # modal_u = mix term + R_hat (Z + I0)
+        ops.spmm_narrow(adj.iu, xu, chains=2, out=modal[nu:], beta=1.0)                        # modal_i
+        if m.gnn_layer >= 1:
+            ops.spmm_narrow(adj.full, modal, chains=2, out=self.buf["last_c"])
+        ss = ops.rows_sumsq(modal, out=self.buf["ss"])
+        ops.cols_push(ss.view(-1, 4), 4, self.peer["ss_all"].ptr_table, self.world, 4, dst_row_offset=self.rank * (self.n_pad // 4),
+                      tag="norms")
+
+    def _p2(self):
+        m = self.model
+        nu, dc, W = m.n_users, self.dc, self.world
+        modal, last, emb = self.buf["modal_c"], self.buf["last_c"], self.buf["emb_c"]
+        ss_all = self.peer["ss_all"].tensor
+        ops.rows_axpby_ss(modal, last if m.gnn_layer >= 1 else None, modal, ss_parts=ss_all, n_parts=W, ss_stride=self.n_pad,
+                          a=1.0, b=1.0 if m.gnn_layer >= 1 else 0.0, c=m.ris_lambda, out=emb)
+        for _ in range(max(0, m.gnn_layer - 1)):
+            nxt = ops.spmm_narrow(m.norm_adj.full, last, chains=2)
+            ops.rows_axpby_ss(emb, nxt, a=1.0, b=1.0, out=emb)
+            last = nxt
+        # column slabs, each stored contiguously into slab `rank` of every peer (items) / of the peer that scores the rows (users)
+        ni = m.n_items
+        ops.cols_push(emb[nu:], dc, self.peer["items_slab"].ptr_table, W, dc, dst_row_offset=self.rank * ni, tag="items")
+        ops.cols_push(emb[:nu], dc, self.peer["users_slab"].ptr_table, W, dc, row_bounds=self.ub_dev,
+                      dst_row_offset=self.rank * self.max_ub, tag="users")
+
+    def _p3(self):
+        """After the last barrier: the slabs the peers stored, side by side as 64-column rows (local)."""
+        m, W, dc = self.model, self.world, self.dc
+        ops.slabs_to_rows(self.peer["items_slab"].tensor, W, m.n_items, m.n_items, dc, self.buf["items_all"])
+        ops.slabs_to_rows(self.peer["users_slab"].tensor, W, self.max_ub, self.u1 - self.u0, dc, self.buf["users_blk"])
+
+    def _result(self):
+        return self.buf["users_blk"][:self.u1 - self.u0], self.buf["items_all"]
+
+    @torch.no_grad()
+    def eval_factors(self):
+        """(user rows of this rank's block, full item table), both 64 columns wide, ready for the fused scoring."""
+        self._p0()
+        self._sync()
+        self._p1()
+        self._sync()
+        self._p2()
+        self._sync()
+        self._p3()
+        return self._result()
+
+    def forward_MM(self, push_items=False):
+        ue, ie = self.eval_factors()
+        return ue, ie[self.i0:self.i1]
+
+    def close(self):
+        for b in self.peer.values():
+            b.close()
+        if self.barrier is not None:
+            self.barrier.close()
+
+
 class ShardedGCNChain(object):
     """Row-sharded LightGCN-style propagation  c = sum_g w_g * mean_{l=0..L} G^l E0  over one or more N x N graphs:
     ``LightGCN.forward`` (GenMMRec/src/models/lightgcn.py:115-127, one graph) and the content embedding GenRecV1

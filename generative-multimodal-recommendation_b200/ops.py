@@ -168,6 +168,39 @@ class GraphCSR:
             self._plan = h
         return self._plan
 
+    @property
+    def narrow_plan(self):
+        """The plan with its length-sorted virtual-row order (what ``spmm_narrow`` walks), built once."""
+        if not self.__dict__.get("_narrow_ready"):
+            lib = _lib.load()
+            with torch.cuda.device(self.device):
+                _lib.check(lib.gmr_spmm_plan_enable_narrow(self.plan, _ptr(self.rowptr), _stream()), "gmr_spmm_plan_enable_narrow")
+            self._narrow_ready = True
+        return self.plan
+
+    def sell(self, d, chains):
+        """Sliced-ELL snapshot for ``spmm_narrow`` with rows of ``d`` floats (csrc/spmm.cu): built once per lane layout,
+        values re-read when ``val`` was modified in place since."""
+        lib = _lib.load()
+        rpw = 32 // ((d // 4) * chains)
+        if "_sells" not in self.__dict__:
+            self._sells = {}
+        key = (rpw, int(chains))   # the snapshot stores a block chain-major: one per lane layout AND chain count
+        ent = self._sells.get(key)
+        with torch.cuda.device(self.device):
+            if ent is None:
+                h = C.c_void_p()
+                _lib.check(lib.gmr_spmm_sell_create(C.byref(h), self.plan, _ptr(self.rowptr), _ptr(self.col), _ptr(self.val),
+                                                    int(d), int(chains), _stream()), "gmr_spmm_sell_create")
+                ent = [h, self.val._version]
+                self._sells[key] = ent
+                self._narrow_ready = True
+            elif ent[1] != self.val._version:
+                _lib.check(lib.gmr_spmm_sell_set_values(ent[0], _ptr(self.rowptr), _ptr(self.col), _ptr(self.val), _stream()),
+                           "gmr_spmm_sell_set_values")
+                ent[1] = self.val._version
+        return ent[0]
+
     def blocked_plan(self, block_cols):
         """Column-blocked plan (K1b, csrc/spmm_flat.cu) with blocks of `block_cols` columns.  The plan snapshots the
         matrix; if `val` was modified in place since (its torch version counter moved) the values are re-read."""
@@ -211,6 +244,8 @@ class GraphCSR:
             if self._plan is not None and _lib._lib is not None:
                 _lib._lib.gmr_spmm_plan_destroy(self._plan)
             if _lib._lib is not None:
+                for h, _ in self.__dict__.get("_sells", {}).values():
+                    _lib._lib.gmr_spmm_sell_destroy(h)
                 for h, _ in self._bplans.values():
                     _lib._lib.gmr_spmm_blocked_plan_destroy(h)
         except Exception:
@@ -332,6 +367,113 @@ def rows_axpby_norm(x, y=None, z=None, a=1.0, b=0.0, c=0.0, eps=1e-12, out=None)
     with torch.cuda.device(x.device):
         _lib.check(lib.gmr_rows_axpby_norm_f32(xp, ldx, yp, ldy, zp, ldz, op, ldo, x.shape[0], x.shape[1], float(a),
                                                float(b), float(c), float(eps), _stream()), "gmr_rows_axpby_norm_f32")
+    LAUNCHES += 1
+    return out
+
+
+def spmm_narrow(a, x, chains=2, out=None, alpha=1.0, beta=0.0, sell=None):
+    """Y = alpha * A @ X + beta * Y for rows of 8 / 16 / 32 / 64 floats (the column shard a rank owns under
+    ``dist.ColShardedDiffMM``): several virtual rows per warp, per-column operation order of the wide kernel
+    (``chains=2``: what ``spmm_raw`` does up to 64 columns; ``chains=1``: what it does for 65..128), so the result equals
+    the corresponding columns of the wide product bit for bit."""
+    global LAUNCHES
+    lib = _lib.load()
+    if x.shape[0] != a.shape[1]:
+        raise ValueError("spmm: A is %s but X has %d rows" % (a.shape, x.shape[0]))
+    d = int(x.shape[1])
+    if out is None:
+        if beta != 0.0:
+            raise ValueError("spmm: beta != 0 needs an `out` to accumulate into")
+        out = torch.empty((a.shape[0], d), dtype=torch.float32, device=x.device)
+    xp, ldx = _rows(x, "X")
+    yp, ldy = _rows(out, "Y")
+    if out.shape != (a.shape[0], d):
+        raise ValueError("spmm: out has shape %s, expected %s" % (tuple(out.shape), (a.shape[0], d)))
+    if sell is None:
+        sell = os.environ.get("GMR_SPMM_SELL", "1") != "0"
+    plan = a.plan
+    snap = a.sell(d, chains) if sell else None   # sliced-ELL snapshot (default) or the CSR stream as it is
+    if snap is None:
+        plan = a.narrow_plan
+    need = lib.gmr_spmm_workspace_bytes(plan, d)
+    ws = _ws(x.device, need, "spmm") if need > 0 else None
+    with torch.cuda.device(x.device):
+        ev = _prof_begin()
+        if snap is not None:
+            _lib.check(lib.gmr_spmm_sell_f32(snap, xp, ldx, yp, ldy, d, int(chains), float(alpha), float(beta), _ptr(ws), need,
+                                             _stream()), "gmr_spmm_sell_f32")
+        else:
+            _lib.check(lib.gmr_spmm_narrow_f32(plan, _ptr(a.rowptr), _ptr(a.col), _ptr(a.val), xp, ldx, yp, ldy, d, int(chains),
+                                               float(alpha), float(beta), _ptr(ws), need, _stream()), "gmr_spmm_narrow_f32")
+        _prof_end("spmm", ev, alg_bytes=a.algorithmic_bytes(d), nnz=a.nnz, d=d, rows=a.shape[0], cols=a.shape[1],
+                  kernel="%s/%d" % ("sell" if snap is not None else "narrow", chains))
+    LAUNCHES += 1 + (1 if need > 0 else 0)
+    return out
+
+
+def cols_push(src, dc, ptr_table, n_peers, ldy, src_col0=0, src_col_step=0, row_bounds=None, dst_row_offset=0, dst_col0=0, tag="",
+              n_seg=1, src_seg_step=0, dst_seg_step=0):
+    """Column-slice copies into peer buffers (``gmr_cols_push_f32``): for every peer p and source row r,
+    ``peer[p][dst_row_offset + r - first_p, dst_col0 : dst_col0 + dc] = src[r, src_col0 + p * src_col_step : ... + dc]``;
+    with ``row_bounds`` (device int64 [n_peers + 1]) row r goes only to the peer whose range holds it; ``n_seg`` segments
+    (source columns ``src_seg_step`` apart, destination columns ``dst_seg_step`` apart) move in one launch."""
+    global LAUNCHES
+    lib = _lib.load()
+    sp, ld = _rows(src, "src")
+    with torch.cuda.device(src.device):
+        ev = _prof_begin()
+        _lib.check(lib.gmr_cols_push_f32(sp, ld, int(src.shape[0]), int(dc), int(src_col0), int(src_col_step),
+                                         C.c_void_p(ptr_table.data_ptr()), int(n_peers), _ptr(row_bounds), int(dst_row_offset),
+                                         int(ldy), int(dst_col0), int(n_seg), int(src_seg_step), int(dst_seg_step), _stream()),
+                   "gmr_cols_push_f32")
+        _prof_end("cols_push" + (":" + tag if tag else ""), ev,
+                  bytes=4.0 * src.shape[0] * dc * n_seg * (1 if row_bounds is not None else n_peers),
+                  peers=int(n_peers))
+    LAUNCHES += 1
+
+
+def slabs_to_rows(slabs, n_slabs, slab_rows, n_rows, dc, out):
+    """out[r, p * dc : (p + 1) * dc] = slab p's row r, for the ``n_slabs`` contiguous [slab_rows, dc] slabs of ``slabs``."""
+    global LAUNCHES
+    lib = _lib.load()
+    op, ldo = _rows(out, "out")
+    with torch.cuda.device(out.device):
+        ev = _prof_begin()
+        _lib.check(lib.gmr_slabs_to_rows_f32(_ptr(slabs), int(n_slabs), int(slab_rows) * int(dc), int(n_rows), int(dc), op, ldo,
+                                             _stream()), "gmr_slabs_to_rows_f32")
+        _prof_end("slabs_to_rows", ev, bytes=8.0 * n_rows * dc * n_slabs)
+    LAUNCHES += 1
+    return out
+
+
+def rows_sumsq(z, out=None):
+    """out[r] = sum_d z[r, d]^2 (a rank's part of the squared row norms; D in 4, 8, 16, 32, 64)."""
+    global LAUNCHES
+    lib = _lib.load()
+    zp, ldz = _rows(z, "z")
+    if out is None:
+        out = torch.empty(z.shape[0], dtype=torch.float32, device=z.device)
+    with torch.cuda.device(z.device):
+        _lib.check(lib.gmr_rows_sumsq_f32(zp, ldz, int(z.shape[0]), int(z.shape[1]), _ptr(out), _stream()), "gmr_rows_sumsq_f32")
+    LAUNCHES += 1
+    return out
+
+
+def rows_axpby_ss(x, y=None, z=None, ss_parts=None, n_parts=1, ss_stride=0, a=1.0, b=0.0, c=0.0, eps=1e-12, out=None):
+    """out = a*x + b*y + c * z / max(sqrt(ss), eps) with ss[r] the balanced-tree sum of ``ss_parts[k * ss_stride + r]``,
+    k < n_parts: ``rows_axpby_norm`` for a column shard whose row norms were formed across the ranks."""
+    global LAUNCHES
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty_like(x)
+    xp, ldx = _rows(x, "x")
+    yp, ldy = _rows(y, "y") if y is not None else (C.c_void_p(0), 0)
+    zp, ldz = _rows(z, "z") if z is not None else (C.c_void_p(0), 0)
+    op, ldo = _rows(out, "out")
+    with torch.cuda.device(x.device):
+        _lib.check(lib.gmr_rows_axpby_ss_f32(xp, ldx, yp, ldy, zp, ldz, _ptr(ss_parts), int(n_parts), int(ss_stride), op, ldo,
+                                             x.shape[0], x.shape[1], float(a), float(b), float(c), float(eps), _stream()),
+                   "gmr_rows_axpby_ss_f32")
     LAUNCHES += 1
     return out
 

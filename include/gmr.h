@@ -234,6 +234,76 @@ int gmr_bpr_scores_backward_f32(const float* Eu, int64_t ldu, const float* Ei, i
                                 const float* g_neg, float* dEu, int64_t lddu, float* dEi, int64_t lddi, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Column-sharded propagation (the multi-GPU form of the same torch.sparse.mm call sites: rank g owns
+ * columns [g * dc, (g + 1) * dc) of every embedding row; A X is column-separable, so the SpMM layers
+ * need no collective).
+ *
+ * gmr_spmm_narrow_f32: K1 for rows of D = 8 / 16 / 32 / 64 floats.  A warp walks 32 / (D/4 * chains)
+ * virtual rows at once (taken in descending-length order, gmr_spmm_plan_enable_narrow builds that
+ * order once per plan and synchronises `stream`).  Per-column operation order is the wide
+ * kernels': chains = 2 -> even / odd nonzeros in two sequential fmaf chains added at the end (what
+ * gmr_spmm_csr_f32 does for D <= 64), chains = 1 -> one chain (what it does for 64 < D <= 128).
+ * A column slice of the narrow product therefore equals the wide product's columns bit for bit.
+ * X / Y rows 16-byte aligned, ldx / ldy multiples of 4; workspace as gmr_spmm_workspace_bytes(plan, D).
+ * ------------------------------------------------------------------------------------------- */
+int gmr_spmm_plan_enable_narrow(gmr_spmm_plan_t* plan, const int32_t* rowptr, void* stream);
+int gmr_spmm_narrow_f32(const gmr_spmm_plan_t* plan, const int32_t* rowptr, const int32_t* col, const float* val,
+                        const float* X, int64_t ldx, float* Y, int64_t ldy, int32_t D, int32_t chains, float alpha,
+                        float beta, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Sliced-ELL snapshot for the narrow product: the (col, val) pairs of the 32 / (D/4 * chains) rows a warp walks
+ * together, interleaved per iteration of 8 entries, rows in descending-length order -- one coalesced load per lane
+ * and iteration instead of scattered CSR reads (the gathers of a column shard are bound by the L1 request rate, so
+ * every request the index stream does not take is a gather gained).  The snapshot copies the matrix (col, val;
+ * gmr_spmm_sell_set_values re-reads them after an in-place value change), is tied to one (D, chains) lane layout
+ * and keeps a pointer to `plan`, which must outlive it.  Same results, bit for bit, as gmr_spmm_narrow_f32. */
+typedef struct gmr_spmm_sell gmr_spmm_sell_t;
+int gmr_spmm_sell_create(gmr_spmm_sell_t** sell, gmr_spmm_plan_t* plan, const int32_t* rowptr, const int32_t* col,
+                         const float* val, int32_t D, int32_t chains, void* stream);
+int gmr_spmm_sell_set_values(gmr_spmm_sell_t* sell, const int32_t* rowptr, const int32_t* col, const float* val, void* stream);
+int gmr_spmm_sell_destroy(gmr_spmm_sell_t* sell);
+int64_t gmr_spmm_sell_bytes(const gmr_spmm_sell_t* sell);
+int gmr_spmm_sell_f32(const gmr_spmm_sell_t* sell, const float* X, int64_t ldx, float* Y, int64_t ldy, int32_t D,
+                      int32_t chains, float alpha, float beta, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Layout changes between row blocks and column blocks by peer stores.  For every peer p (y_peers is a DEVICE
+ * array of n_peers <= 16 peer-mapped base pointers), every source row r and every segment s < n_seg:
+ *   y_peers[p][(dst_row_offset + r - first_p) * ldy + dst_col0 + s * dst_seg_step + c]
+ *       = src[r * ld + src_col0 + s * src_seg_step + p * src_col_step + c],  c < dc
+ * row_bounds == NULL: every row goes to every peer (first_p = 0) -- an all-to-all of column slices when
+ * src_col_step = dc, an all-gather of one slice when it is 0.  row_bounds = DEVICE int64[n_peers + 1]: row r goes
+ * only to the peer with row_bounds[p] <= r < row_bounds[p + 1] (first_p = row_bounds[p]).  All widths and
+ * offsets multiples of 4 floats, 16-byte aligned buffers.  The caller synchronises the ranks. */
+int gmr_cols_push_f32(const float* src, int64_t ld, int64_t n_rows, int32_t dc, int64_t src_col0, int64_t src_col_step,
+                      float* const* y_peers, int32_t n_peers, const int64_t* row_bounds, int64_t dst_row_offset,
+                      int64_t ldy, int64_t dst_col0, int32_t n_seg, int64_t src_seg_step, int64_t dst_seg_step, void* stream);
+
+/* out[r, p * dc + c] = slabs[p * slab_stride + r * dc + c]: n_slabs column slabs of [n_rows, dc] (what the peers stored,
+ * each contiguously -- NVLink moves full lines ~3x faster than 32-byte granules at a row pitch) side by side as rows. */
+int gmr_slabs_to_rows_f32(const float* slabs, int32_t n_slabs, int64_t slab_stride, int64_t n_rows, int32_t dc, float* out,
+                          int64_t ldo, void* stream);
+
+/* out[r] = sum_d z[r, d]^2 over D = 4 / 8 / 16 / 32 / 64 columns: a rank's part of the squared row norm of
+ * F.normalize (GenMMRec/src/models/diffmm.py:166), summed as the subtree of gmr_rows_axpby_norm_f32's (D = 64)
+ * reduction tree that covers an aligned block of D columns. */
+int gmr_rows_sumsq_f32(const float* z, int64_t ldz, int64_t n_rows, int32_t D, float* out, void* stream);
+
+/* out[r, :] = a * x[r, :] + b * y[r, :] + c * z[r, :] / max(sqrt(ss[r]), eps),  ss[r] = the n_parts (a power of two
+ * <= 16) values ss_parts[k * ss_stride + r] added as a balanced tree, neighbours first -- together with
+ * gmr_rows_sumsq_f32 the same bits as gmr_rows_axpby_norm_f32 on the full 64-column row.  y, z may be NULL;
+ * out may alias x, y or z; D % 4 == 0, 16-byte aligned rows. */
+int gmr_rows_axpby_ss_f32(const float* x, int64_t ldx, const float* y, int64_t ldy, const float* z, int64_t ldz,
+                          const float* ss_parts, int32_t n_parts, int64_t ss_stride, float* out, int64_t ldo,
+                          int64_t n_rows, int32_t D, float a, float b, float c, float eps, void* stream);
+
+/* Stream-ordered cross-rank barrier through peer memory: flags_peers is a DEVICE array of n_ranks pointers to
+ * every rank's uint32[n_ranks] flag array (zero-initialised, peer-mapped), state a LOCAL device uint32[2]
+ * (zero-initialised): state[0] counts the barriers passed, state[1] the times a peer did not arrive within ~4 s
+ * (the kernel then gives up instead of hanging the GPU; the host should check it).  Everything this rank's earlier
+ * kernels on `stream` stored into peer buffers is visible to a peer once it has passed the barrier. */
+int gmr_peer_barrier(uint32_t* const* flags_peers, int32_t my_rank, int32_t n_ranks, uint32_t* state, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Peer-memory plumbing for the fused SpMM + all-gather (CUDA IPC, one process per GPU).
  * gmr_peer_alloc allocates `bytes` of device memory suitable for export; gmr_peer_export fills a
  * 64-byte handle; another process maps it with gmr_peer_open.  The Python host exchanges the

@@ -18,10 +18,10 @@ pytestmark = pytest.mark.gpu
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(model, shape, nproc, port, layers=2):
+def _run(model, shape, nproc, port, layers=2, mode="rows"):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr",
            "127.0.0.1", "--master-port", str(port), os.path.join(REPO, "tools", "dist_check.py"), "--model", model, "--shape",
-           shape, "--layers", str(layers)]
+           shape, "--layers", str(layers), "--mode", mode]
     p = subprocess.run(cmd, cwd=REPO, capture_output=True, text=True, timeout=900)
     rows, dec = [], json.JSONDecoder()
     for ln in p.stdout.splitlines():      # tolerate two ranks' records landing on one line
@@ -44,4 +44,15 @@ def test_sharded_equals_single_gpu(model, shape):
     for r in rows:
         # the sharded dataflow runs the same kernels on row blocks: rows are bit-identical in practice
         assert r["user_rows_rel_err"] == 0.0 and r["gathered_items_rel_err"] == 0.0, r
+        assert r["topk_rows_identical"] == 1.0 and r["metric_sums_match"], r
+
+
+def test_column_sharded_diffmm_equals_single_gpu():
+    """Embedding columns sharded over real ranks (dist.ColShardedDiffMM: narrow SpMM passes over the whole graph, column
+    slices exchanged by peer stores, flag barriers in peer memory): user blocks and item table bit-identical to one GPU."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs at least two GPUs")
+    rows = _run("DiffMM", "baby", 2, 29589, mode="cols")
+    for r in rows:
+        assert r["mode"] == "cols" and r["bit_identical"], r
         assert r["topk_rows_identical"] == 1.0 and r["metric_sums_match"], r

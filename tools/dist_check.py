@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--shape", default="baby")
     ap.add_argument("--model", default="DiffMM", choices=["DiffMM", "GenRecV1", "LightGCN"])
     ap.add_argument("--layers", type=int, default=2)
+    ap.add_argument("--mode", default="rows", choices=["rows", "cols"], help="DiffMM: adjacency rows or embedding columns sharded")
     args = ap.parse_args()
     from genmmrec_b200 import dist as gd, ops
     from genmmrec_b200.common.trainer import Trainer
@@ -40,7 +41,7 @@ def main():
         ue, ie = model.propagate()
         ids_ref, _ = trainer.topk_all(wl.valid)
         sums_ref, _ = trainer.evaluator.metric_sums(ids_ref, wl.valid)
-        sh = {"DiffMM": gd.ShardedDiffMM, "GenRecV1": gd.sharded_genrecv1, "LightGCN": gd.sharded_lightgcn}[args.model](model)
+        sh = {"DiffMM": gd.ColShardedDiffMM if args.mode == "cols" else gd.ShardedDiffMM, "GenRecV1": gd.sharded_genrecv1, "LightGCN": gd.sharded_lightgcn}[args.model](model)
         for _ in range(2):  # twice: buffers are reused across calls
             su, items = sh.eval_factors()
         part = gd.shard_eval_by_user_block(wl.valid, sh.u0, sh.u1)
@@ -57,7 +58,10 @@ def main():
     same_rows = float((ids == ids_ref[part.positions]).all(dim=1).float().mean())
     ok_ids = same_rows > 0.98
     ok_m = bool((sums - sums_ref).abs().max() < 1e-3 * sums_ref.abs().max())
-    res = {"rank": rank, "world": world, "users_block": [sh.u0, sh.u1], "items_block": [sh.i0, sh.i1],
+    if getattr(sh, "barrier", None) is not None:
+        sh.barrier.check()
+    res = {"rank": rank, "world": world, "mode": args.mode if args.model == "DiffMM" else "rows",
+           "bit_identical": bool(torch.equal(su, ue[sh.u0:sh.u1]) and torch.equal(items, ie)), "users_block": [sh.u0, sh.u1], "items_block": [sh.i0, sh.i1],
            "user_rows_rel_err": tol_u, "gathered_items_rel_err": tol_i, "topk_rows_identical": same_rows,
            "metric_sums_match": ok_m}
     sys.stdout.flush()
