@@ -38,6 +38,13 @@
 //   5. end of a user tile: prune, exact fp32 fmaf re-score of the survivors, sort by (score desc, id asc),
 //      write the top K.  Rows whose buffer overflowed (massive near-ties), rows with fewer than K
 //      unmasked items and rows with non-finite scores are queued for the fp32 kernel.
+//   0. exact HEAD (before any of the above, no bias, K <= 128): the n_hot = 128 / 256 highest-norm items are scored
+//      EXACTLY for every row by a register-tiled CUDA-core product whose per-score operation order is the oracle's
+//      sequential fmaf chain; the row's exact K-th best head score s_K is compared with the Cauchy-Schwarz bound of
+//      everything outside the head, |u| * nb[n_hot]: if the bound is smaller the head's top K IS the answer and the
+//      row is written and flagged done -- no screen, no intervals, no re-score.  With popularity-skewed embeddings
+//      that settles ~98 % of the rows; the screen pipeline then only touches 256-user groups with a live row.  With
+//      flat norms (nb[n_hot] >= nb[K-1]: no row can finish) the head switches itself off on the device.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -257,11 +264,17 @@ struct RowConst {
 __global__ void __launch_bounds__(256)
     prep_users_kernel(const float* __restrict__ E, int64_t lde, const int64_t* __restrict__ rows, int32_t n_rows,
                       int32_t n_rows_pad, int32_t D, const uint32_t* __restrict__ gmax_bits, const float* __restrict__ nb,
-                      const uint32_t* __restrict__ biasmax_bits, __half* __restrict__ out, RowConst* __restrict__ row_const)
+                      const uint32_t* __restrict__ biasmax_bits, const uint8_t* __restrict__ row_done,
+                      __half* __restrict__ out, RowConst* __restrict__ row_const)
 {
     const int lane = threadIdx.x & 31;
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= n_rows_pad) return;
+    if (r < n_rows && row_done[r]) {
+        // settled by the exact head: its fp16 row is never looked at (a stale row only feeds its own accumulators)
+        if (lane == 0) row_const[r] = RowConst{0.f, 0.f, INFINITY, 0.f};
+        return;
+    }
     __half* o = out + r * (int64_t)D;
     const float* src = (r < n_rows) ? E + (rows ? rows[r] : r) * lde : nullptr;
     // the row stays in registers between the absmax pass and the conversion (D <= 256: 4 x float2 per lane)
@@ -325,7 +338,8 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     prep_users_d64_kernel(const float* __restrict__ E, int64_t lde, const int64_t* __restrict__ rows, int32_t n_rows,
                           int32_t n_rows_pad, const uint32_t* __restrict__ gmax_bits, const float* __restrict__ nb,
-                          const uint32_t* __restrict__ biasmax_bits, __half* __restrict__ out, RowConst* __restrict__ row_const)
+                          const uint32_t* __restrict__ biasmax_bits, const uint8_t* __restrict__ row_done,
+                          __half* __restrict__ out, RowConst* __restrict__ row_const)
 {
     const int lane = threadIdx.x & 31, sub = lane & 15, half = lane >> 4;
     const int64_t r0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 8 + half;
@@ -333,7 +347,8 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int64_t r = r0 + 2 * q;
-        src[q] = r < n_rows ? (rows ? rows[r] : r) : -1;
+        // rows settled by the exact head are not read: their fp16 row only feeds their own (ignored) accumulators
+        src[q] = (r < n_rows && !row_done[r]) ? (rows ? rows[r] : r) : -1;
     }
     float4 x[4];
 #pragma unroll
@@ -370,6 +385,7 @@ __global__ void __launch_bounds__(256)
                 rc.ab += 2.4e-7f * rc.sc * __uint_as_float(*biasmax_bits);
             }
             rc.na = na;
+            if (r < n_rows && row_done[r]) rc = RowConst{0.f, 0.f, INFINITY, 0.f};
             row_const[r] = rc;
         }
     }
@@ -553,6 +569,7 @@ struct ScrArgs {
     int32_t n_stages;
     int32_t vec4;               // Eu / Ei rows are 16-byte aligned
     int32_t first_check;        // tiles swept before the first stop check (phase 0)
+    uint8_t* row_done;          // [B_pad] 1: the exact head already wrote the row's top K
     unsigned long long* stats;  // [kStatSlots] or null
     int32_t debug;              // GMR_TC_DEBUG timing experiments: 1 = drain TMEM only, 2 = filter without appends,
                                 // 3 = no early stop (full sweep; results stay exact)
@@ -659,6 +676,312 @@ __device__ __forceinline__ void rescore_sort_write(const ScrArgs& a, const float
     final_sort_write<NSORT>(ek, lane, a, rb);
 }
 
+// ---- 3.0 the exact head ---------------------------------------------------------------------------------
+struct HeadArgs {
+    const float* nb_sorted;     // [I] UNSCALED item norms in sweep order (rounded up), as the sort left them
+    const int32_t* perm_sorted; // [I] sweep position -> item id
+    uint16_t* hot_pos;          // [I] item id -> head position, 0xFFFF outside the head (memset before head_setup)
+    int32_t* hot_id;            // [n_hot] head position -> item id (-1: past the catalogue)
+    uint32_t* hot_bits;         // [ceil(I / 32)] bit i: item i is in the head (an L1-resident filter in front of hot_pos)
+    uint32_t* row_bits;         // [B_pad][n_hot / 32] bit p of row b: head position p is in b's train history
+    float* bound;               // [1] unscaled norm of the first item OUTSIDE the head (0: the head is the catalogue)
+    int32_t* on;                // [1] 0: no row can finish in the head (flat norms) -- the head kernel returns at once
+    int32_t n_hot;
+    float margin;               // (1 + rounding slack of the norms and of the fp32 score chains)
+};
+
+__global__ void __launch_bounds__(256) score_head_setup_kernel(HeadArgs h, int32_t I, int32_t K)
+{
+    for (int p = threadIdx.x; p < h.n_hot; p += blockDim.x) {
+        const int item = p < I ? h.perm_sorted[p] : -1;
+        h.hot_id[p] = item;
+        if (item >= 0) {
+            h.hot_pos[item] = (uint16_t)p;
+            atomicOr(&h.hot_bits[item >> 5], 1u << (item & 31));
+        }
+    }
+    if (threadIdx.x == 0) {
+        const float out = h.n_hot < I ? h.nb_sorted[h.n_hot] : 0.f;
+        *h.bound = out;
+        // s_K <= |u| * (K-th largest norm): a row can only finish if the outside bound is below that
+        // (a computed norm below ~1e-15 may have lost squares to underflow and is no longer a bound: head off)
+        const bool can = (I <= h.n_hot) || (K <= I && out >= 1e-15f && out * h.margin < h.nb_sorted[K - 1]);
+        *h.on = can ? 1 : 0;
+    }
+}
+
+// row_bits of every row from the train-history CSR.  ENTRY-parallel: a warp owns 1,024 consecutive CSR entries whatever
+// rows they belong to (a user with 10^5 interactions costs what 2,000 users with 50 cost; walking the lists row by row
+// inside the head kernel made its longest row -- n_items / 4 entries in the synthetic workloads -- the kernel's duration).
+// The two rows that bracket the chunk come from a binary search of the row pointers; a hit (about one entry in seven
+// passes the hot_bits filter) finds its own row inside that bracket.
+constexpr int kMaskChunk = 1024;
+__global__ void __launch_bounds__(256)
+    score_head_maskbits_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ items, int64_t B, HeadArgs h,
+                               const uint8_t* __restrict__ unused)
+{
+    (void)unused;
+    if (*h.on == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t base = rowptr[0], end = rowptr[B];
+    const int words = h.n_hot >> 5;
+    // the host does not know the number of entries: a fixed grid strides over the chunks
+    for (int64_t j0 = base + ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * kMaskChunk; j0 < end;
+         j0 += (int64_t)gridDim.x * 8 * kMaskChunk) {
+    const int64_t j1 = (j0 + kMaskChunk < end) ? j0 + kMaskChunk : end;
+    // lane 0: row of entry j0, lane 1: row of entry j1 - 1 (last r with rowptr[r] <= target; empty rows are skipped)
+    int64_t lo = 0;
+    {
+        const int64_t target = lane == 0 ? j0 : j1 - 1;
+        int64_t hi = B;
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (rowptr[mid] <= target) lo = mid; else hi = mid;
+        }
+    }
+    const int64_t r0 = __shfl_sync(0xffffffffu, lo, 0), r1 = __shfl_sync(0xffffffffu, lo, 1);
+    for (int64_t jb = j0; jb < j1; jb += 128) {
+        int32_t it[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int64_t j = jb + q * 32 + lane;
+            it[q] = j < j1 ? items[j] : -1;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (it[q] < 0 || !((h.hot_bits[it[q] >> 5] >> (it[q] & 31)) & 1u)) continue;
+            const int64_t j = jb + q * 32 + lane;
+            const uint32_t p = h.hot_pos[it[q]];
+            int64_t a = r0, b = r1 + 1;   // rowptr[a] <= j < rowptr[b]
+            while (b - a > 1) {
+                const int64_t mid = (a + b) >> 1;
+                if (rowptr[mid] <= j) a = mid; else b = mid;
+            }
+            atomicOr(&h.row_bits[a * words + (p >> 5)], 1u << (p & 31));
+        }
+    }
+    }
+}
+
+// Bitonic sort of 16 * P keys owned by a HALF-warp, descending: lane `sub` (0 .. 15 inside its half) holds the elements
+// sub * P .. sub * P + P - 1, so the log2(P) smallest strides of every merge are register-local compare-exchanges (no
+// shuffle, no redundant compare) and only strides >= P cross lanes (xor masks < 16 stay inside the half).
+template <int P>
+__device__ __forceinline__ void halfwarp_bitonic_sort_desc(uint64_t (&k)[P], int sub)
+{
+    constexpr int N = 16 * P;
+#pragma unroll
+    for (int size = 2; size <= N; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= P) {
+                const int ls = stride / P;
+                const bool take_max = (((sub * P) & size) == 0) == ((sub & ls) == 0);   // size > stride >= P: no r bits
+#pragma unroll
+                for (int r = 0; r < P; ++r) {
+                    const uint64_t other = __shfl_xor_sync(0xffffffffu, k[r], ls);
+                    k[r] = ((k[r] > other) == take_max) ? k[r] : other;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < P; ++r) {
+                    if ((r & stride) == 0) {
+                        const int r2 = r | stride;
+                        const bool desc = size < P ? ((r & size) == 0) : ((((sub * P) | r) & size) == 0);
+                        const uint64_t x = k[r], y = k[r2];
+                        const bool sw = (x > y) != desc;   // descending block: larger key first
+                        k[r] = sw ? y : x;
+                        k[r2] = sw ? x : y;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// One warp owns R = 32 / NKEY rows at a time.  Phase A (row loads, norms, masked-position bitmaps: the loads of the R
+// rows are issued together), phase B (register-tiled exact scores: lane l holds head items l, l + 32, ...), phase C
+// (selection: scores go through shared memory to a half-warp-per-row layout; the loop over row pairs is NOT unrolled --
+// the first version unrolled the sort network R times, 30,800 SASS instructions, and ran at 27 % issue-active on
+// instruction-cache misses).
+template <int NKEY>
+__global__ void __launch_bounds__(256, 2) score_head_kernel(ScrArgs a, HeadArgs h)
+{
+    constexpr int R = 32 / NKEY;
+    constexpr int NH = 32 * NKEY;
+    constexpr int P = NH / 16;                                      // keys per lane in the selection
+    if (*h.on == 0) return;
+    extern __shared__ __align__(16) float head_smem[];
+    const int D = a.D;
+    const int pitch = D + 4;                                        // conflict-free 128-bit reads of 8 different rows
+    float* e_hot = head_smem;                                       // [NH][D + 4]
+    float* u_all = e_hot + (size_t)NH * pitch;                      // [8 warps][R][D]
+    float* sc_all = u_all + 8 * R * D;                              // [8 warps][R][NH] exact scores
+    uint32_t* bm_all = reinterpret_cast<uint32_t*>(sc_all + 8 * R * NH);  // [8 warps][R][NKEY] masked-position bitmaps
+    int32_t* ids = reinterpret_cast<int32_t*>(bm_all + 8 * R * NKEY);     // [NH]
+    float* na_all = reinterpret_cast<float*>(ids + NH);             // [8 warps][R] row norms (rounded up)
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int p = threadIdx.x; p < NH; p += blockDim.x) ids[p] = h.hot_id[p];
+    for (int idx = threadIdx.x; idx < NH * D; idx += blockDim.x) {
+        const int p = idx / D, d = idx - p * D;
+        const int item = h.hot_id[p];
+        e_hot[(size_t)p * pitch + d] = item >= 0 ? a.Ei[(int64_t)item * a.lde_i + d] : 0.f;
+    }
+    __syncthreads();
+    const float bound = *h.bound;
+    const bool whole = a.I <= NH;   // nothing outside the head
+    float* u_w = u_all + (size_t)w * R * D;
+    float* sc_w = sc_all + (size_t)w * R * NH;
+    uint32_t* bm = bm_all + w * R * NKEY;
+    float* na_w = na_all + w * R;
+    unsigned long long n_done = 0;
+    for (int64_t b0 = ((int64_t)blockIdx.x * 8 + w) * R; b0 < a.B; b0 += (int64_t)gridDim.x * 8 * R) {
+        // ---- A. rows -> shared memory, norms, masked head positions ----
+        // lane q < R fetches row q's source index and mask range (one round trip for all R rows)
+        int64_t my_src = 0, my_mlo = 0, my_mhi = 0;   // (the mask range only decides row_force_exact here)
+        bool my_cand = false;
+        {
+            const int64_t b = b0 + (lane < R ? lane : 0);
+            const int64_t bc = b < a.B ? b : a.B - 1;               // rows past the end read the last row, never a candidate
+            my_src = a.users ? a.users[bc] : bc;
+            if (a.mask_rowptr != nullptr) {
+                my_mlo = a.mask_rowptr[bc];
+                my_mhi = a.mask_rowptr[bc + 1];
+            }
+            // masked items would surface: the fp32 kernel owns that case (row_force_exact)
+            my_cand = lane < R && b < a.B && !((int64_t)a.I - (my_mhi - my_mlo) < (int64_t)a.K);
+        }
+        unsigned cand_bits = __ballot_sync(0xffffffffu, my_cand);
+        // masked head positions of the R rows: R * NKEY = 32 consecutive words (score_head_maskbits_kernel; rows past the
+        // end lie inside the padded allocation)
+        const uint32_t my_bits = (a.mask_rowptr != nullptr) ? h.row_bits[b0 * NKEY + lane] : 0u;
+        float ss[R];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) ss[rr] = 0.f;
+        {
+            const float* src[R];
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) src[rr] = a.Eu + __shfl_sync(0xffffffffu, my_src, rr) * a.lde_u;
+            for (int d = lane; d < D; d += 32) {
+                float v[R];
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) v[rr] = src[rr][d];
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) {
+                    u_w[rr * D + d] = v[rr];
+                    ss[rr] = fmaf(v[rr], v[rr], ss[rr]);
+                }
+            }
+        }
+        bm[lane] = my_bits;
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            float t = ss[rr];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            // below 1e-30 the squares underflow and sqrt(ss) is no longer an upper bound of the norm
+            if (!(t >= 1e-30f)) cand_bits &= ~(1u << rr);
+            if (lane == 0) na_w[rr] = sqrtf(t) * 1.000001f;
+        }
+        __syncwarp();
+        // ---- B. exact scores: acc[rr][r] = the oracle's fmaf chain over d = 0 .. D-1 starting from 0 ----
+        {
+            float acc[R][NKEY];
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+                for (int r = 0; r < NKEY; ++r) acc[rr][r] = 0.f;
+#pragma unroll 2
+            for (int d4 = 0; d4 < D / 4; ++d4) {
+                float4 e[NKEY];
+#pragma unroll
+                for (int r = 0; r < NKEY; ++r)
+                    e[r] = *reinterpret_cast<const float4*>(e_hot + (size_t)(r * 32 + lane) * pitch + 4 * d4);
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) {
+                    const float4 u = *reinterpret_cast<const float4*>(u_w + rr * D + 4 * d4);
+#pragma unroll
+                    for (int r = 0; r < NKEY; ++r) {
+                        float s = acc[rr][r];
+                        s = fmaf(u.x, e[r].x, s);
+                        s = fmaf(u.y, e[r].y, s);
+                        s = fmaf(u.z, e[r].z, s);
+                        s = fmaf(u.w, e[r].w, s);
+                        acc[rr][r] = s;
+                    }
+                }
+            }
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+                for (int r = 0; r < NKEY; ++r) sc_w[rr * NH + r * 32 + lane] = acc[rr][r];
+        }
+        __syncwarp();
+        // ---- C. per row (a half-warp each, two rows at a time): keys, sort, stop test ----
+        const int sub = lane & 15, hw = lane >> 4;
+#pragma unroll 1
+        for (int pair = 0; pair < R / 2; ++pair) {
+            const int rr = 2 * pair + hw;
+            const int64_t b = b0 + rr;
+            uint64_t k[P];
+            bool finite = true;
+            {
+                const uint32_t mw = bm[rr * NKEY + ((sub * P) >> 5)] >> ((sub * P) & 31);   // P <= 16 bits of one word
+#pragma unroll
+                for (int r4 = 0; r4 < P / 4; ++r4) {
+                    const float4 s4 = *reinterpret_cast<const float4*>(sc_w + rr * NH + sub * P + 4 * r4);
+                    const int4 i4 = *reinterpret_cast<const int4*>(ids + sub * P + 4 * r4);
+                    const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+                    const int iv[4] = {i4.x, i4.y, i4.z, i4.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const bool ok = iv[q] >= 0 && !((mw >> (4 * r4 + q)) & 1u);
+                        finite = finite && (!ok || fabsf(sv[q]) < INFINITY);
+                        k[4 * r4 + q] = ok ? make_key(sv[q], iv[q]) : 0ull;
+                    }
+                }
+            }
+            const unsigned fin_bits = __ballot_sync(0xffffffffu, finite);
+            const bool all_finite = ((fin_bits >> (16 * hw)) & 0xFFFFu) == 0xFFFFu;
+            halfwarp_bitonic_sort_desc<P>(k, sub);
+            const int kth = a.K - 1;   // K <= NH / 2
+            // the K-th key's score word through shared memory (a register array indexed by kth % P would live in local
+            // memory); 0 = fewer than K unmasked head items (no finite score orders to 0)
+            __syncwarp();
+            uint32_t* so = reinterpret_cast<uint32_t*>(sc_w + rr * NH);
+#pragma unroll
+            for (int r = 0; r < P; ++r) so[sub * P + r] = (uint32_t)(k[r] >> 32);
+            __syncwarp();
+            const uint32_t kk = so[kth];
+            // every item outside the head scores (as computed in fp32) at most |u| * bound * margin
+            const float na = na_w[rr];
+            const bool done = b < a.B && ((cand_bits >> rr) & 1u) && all_finite && kk != 0u && na < INFINITY &&
+                              (whole || na * bound * h.margin < ordered_to_f32(kk));
+            if (done) {
+#pragma unroll
+                for (int r = 0; r < P; ++r) {
+                    const int j = sub * P + r;
+                    if (j < a.K) {
+                        a.out_ids[b * a.K + j] = key_id(k[r]);
+                        if (a.out_scores) a.out_scores[b * a.K + j] = key_score(k[r]);
+                    }
+                }
+                if (sub == 0) n_done += 1;
+            }
+            if (sub == 0 && b < a.B) a.row_done[b] = done ? 1 : 0;
+        }
+        __syncwarp();
+    }
+    if (a.stats != nullptr && n_done) atomicAdd(&a.stats[7], n_done);
+}
+
+static size_t head_smem_bytes(int nkey, int32_t D)
+{
+    const int nh = 32 * nkey, r = 32 / nkey;
+    return (size_t)nh * (D + 4) * 4 + (size_t)8 * r * D * 4 + (size_t)8 * r * nh * 4 + (size_t)8 * r * nkey * 4 + (size_t)nh * 4 +
+           (size_t)8 * r * 4;
+}
+
 // ---- 3a. the sweep kernel (TMA + tcgen05 + screening epilogue) ----------------------------------------
 // phase 0: every 256-user group sweeps tiles [0, first_check) and stores its row state.
 // phase 1: groups whose rows still need tiles (group_need, written by the checkpoint kernel) continue from
@@ -752,6 +1075,12 @@ __global__ void __launch_bounds__(kScrThreads, 1)
             __syncthreads();
         }
         if (ug >= n_groups) break;
+        if (phase == 0) {
+            // groups whose 256 rows were all settled by the exact head are not swept at all
+            const int64_t bb = (int64_t)ug * kRowsPerCta + row_cta;
+            const int live = (warp >= 2 && bb < a.B && !a.row_done[bb]) ? 1 : 0;
+            if (__syncthreads_or(live) == 0) continue;
+        }
         int it = 0, it_end = T0, next_check = 0x7fffffff;
         if (phase == 1) {
             it = T0;
@@ -786,7 +1115,8 @@ __global__ void __launch_bounds__(kScrThreads, 1)
             rc = a.row_const[b];
             const bool fe = row_force_exact(a, b, mlo, mhi);
             if (phase == 0) {
-                L = (fe || !(rc.na < INFINITY)) ? INFINITY : -INFINITY;  // +inf: redone on the fp32 path, collect nothing
+                // +inf: collect nothing (settled by the head, or redone on the fp32 path)
+                L = (fe || !(rc.na < INFINITY) || a.row_done[b]) ? INFINITY : -INFINITY;
             } else {
                 cnt = a.row_cnt[b];
                 chk = a.row_chk[b];
@@ -1001,7 +1331,7 @@ __global__ void __launch_bounds__(256, (NPL == 8) ? 4 : ((NPL == 16) ? 3 : 2))
     constexpr int CAP = 32 * NPL;
     const int lane = threadIdx.x & 31;
     const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (b >= a.B) return;
+    if (b >= a.B || a.row_done[b]) return;
     const int n_itiles = (a.I + kSN - 1) / kSN;
     const int T0 = a.first_check < n_itiles ? a.first_check : n_itiles;
     const RowConst rc = a.row_const[b];
@@ -1051,6 +1381,7 @@ __global__ void __launch_bounds__(256, (NPL == 8) ? 3 : 2)
     __syncthreads();
     float* u_sm = u_all + w * a.D;
     for (int64_t b = (int64_t)blockIdx.x * 8 + w; b < a.B; b += (int64_t)gridDim.x * 8) {
+        if (a.row_done[b]) continue;
         const RowConst rc = a.row_const[b];
         int64_t mlo, mhi;
         const bool fe = row_force_exact(a, b, mlo, mhi);
@@ -1149,7 +1480,7 @@ static size_t scr_sort_temp_bytes(int32_t I)
 
 struct ScrLayout {
     int64_t a_h, b_h, row_const, nb, perm, nb_raw, ident, sort_tmp, misc, fallback, row_cnt, row_chk, row_L, group_need,
-        slots, simt, total;
+        slots, simt, hot_pos, hot_id, row_done, hot_bits, row_bits, total;
     int64_t sort_tmp_bytes;
     int32_t b_pad, i_pad;
 };
@@ -1175,7 +1506,8 @@ static ScrLayout scr_layout(int32_t B, int32_t I, int32_t D, int32_t K)
     L.ident = take((int64_t)L.i_pad * 4);
     L.sort_tmp_bytes = (int64_t)scr_sort_temp_bytes(I);
     L.sort_tmp = take(L.sort_tmp_bytes);
-    L.misc = take(256);  // u32 [0] item absmax bits, [1] fallback count, [3] bias absmax, [4] group scheduler; u64 stats at +64
+    L.misc = take(256);  // u32 [0] item absmax bits, [1] fallback count, [3] bias absmax, [4] group scheduler; u64 stats at +64;
+                         // f32 [32] head bound, i32 [33] head on
     L.fallback = take((int64_t)B * 4);
     L.row_cnt = take((int64_t)L.b_pad * 4);
     L.row_chk = take((int64_t)L.b_pad * 4);
@@ -1183,6 +1515,11 @@ static ScrLayout scr_layout(int32_t B, int32_t I, int32_t D, int32_t K)
     L.group_need = take((int64_t)(L.b_pad / kRowsPerCta) * 4);
     L.slots = take((int64_t)L.b_pad * cap * 8);
     L.simt = take(score_simt_workspace_bytes(B, K));
+    L.hot_pos = take((int64_t)I * 2);
+    L.hot_id = take(256 * 4);
+    L.row_done = take((int64_t)L.b_pad);
+    L.hot_bits = take(((int64_t)I + 31) / 32 * 4);
+    L.row_bits = take((int64_t)L.b_pad * (K <= 64 ? 4 : 8) * 4);
     L.total = off;
     return L;
 }
@@ -1200,7 +1537,8 @@ int score_screen_fallback_count(const void* workspace, int32_t B, int32_t I, int
 }
 
 // diagnostics of the last call with GMR_SCREEN_STATS=1: [0] slow-path chunks, [1] appends, [2] pool prunes,
-// [3] exact prunes, [5] exactly re-scored candidates, [6] item tiles swept (summed over 256-user groups)
+// [3] exact prunes, [5] exactly re-scored candidates, [6] item tiles swept (summed over 256-user groups),
+// [7] rows settled by the exact head
 int score_screen_stats(const void* workspace, int32_t B, int32_t I, int32_t D, int32_t K, uint64_t* stats_host,
                        cudaStream_t st)
 {
@@ -1260,24 +1598,6 @@ int score_topk_screen_launch(const float* Eu, int64_t lde_u, const int64_t* user
         GMR_CHECK_CUDA(cub::DeviceRadixSort::SortPairsDescending(ws + L.sort_tmp, tmp, nb_raw, (uint32_t*)nb, ident, perm, I,
                                                                  0, 32, st));
     }
-    if (items_d64)
-        prep_items_d64_kernel<<<(L.i_pad + 8 * wpb - 1) / (8 * wpb), wpb * 32, 0, st>>>(Ei, lde_i, I, L.i_pad, misc, perm, nb, b_h);
-    else
-        prep_items_kernel<<<(L.i_pad + wpb - 1) / wpb, wpb * 32, 0, st>>>(Ei, lde_i, I, L.i_pad, D, misc, perm, nb, b_h);
-    GMR_LAUNCH_CHECK();
-    if (D == 64 && lde_u % 4 == 0 && (uintptr_t)Eu % 16 == 0)
-        prep_users_d64_kernel<<<(L.b_pad + 8 * wpb - 1) / (8 * wpb), wpb * 32, 0, st>>>(Eu, lde_u, users, B, L.b_pad, misc, nb,
-                                                                                       bias ? misc + 3 : nullptr, a_h, row_const);
-    else
-        prep_users_kernel<<<(L.b_pad + wpb - 1) / wpb, wpb * 32, 0, st>>>(Eu, lde_u, users, B, L.b_pad, D, misc, nb,
-                                                                         bias ? misc + 3 : nullptr, a_h, row_const);
-    GMR_LAUNCH_CHECK();
-
-    CUtensorMap map_a, map_b;
-    if (!scr_make_map(&map_a, a_h, L.b_pad, D) || !scr_make_map(&map_b, b_h, L.i_pad, D)) {
-        set_error("score_topk_screen: cuTensorMapEncodeTiled unavailable or failed");
-        return GMR_ERR_CUDA;
-    }
     ScrArgs a;
     a.Eu = Eu; a.lde_u = lde_u; a.users = users; a.B = B; a.Ei = Ei; a.lde_i = lde_i; a.bias = bias; a.I = I; a.D = D;
     a.mask_rowptr = mask_rowptr; a.mask_items = mask_items; a.K = K; a.out_ids = out_ids; a.out_scores = out_scores;
@@ -1290,6 +1610,60 @@ int score_topk_screen_launch(const float* Eu, int64_t lde_u, const int64_t* user
     a.first_check = (2 * K + kSN - 1) / kSN;  // enough tiles for ~2K candidates before the first stop check
     a.stats = getenv("GMR_SCREEN_STATS") ? (unsigned long long*)(ws + L.misc + 64) : nullptr;
     a.debug = getenv("GMR_TC_DEBUG") ? atoi(getenv("GMR_TC_DEBUG")) : 0;
+    a.row_done = ws + L.row_done;
+    GMR_CHECK_CUDA(cudaMemsetAsync(a.row_done, 0, (size_t)L.b_pad, st));
+    // exact head over the n_hot highest-norm items (sorted norms are still unscaled here); see the file header
+    {
+        const int nkey = K <= 64 ? 4 : 8;
+        const size_t hsmem = head_smem_bytes(nkey, D);
+        const char* env = getenv("GMR_SCREEN_HEAD");
+        const bool head = bias == nullptr && K <= 128 && a.debug == 0 && hsmem <= 200 * 1024 && !(env && atoi(env) == 0);
+        if (head) {
+            HeadArgs h;
+            h.nb_sorted = nb; h.perm_sorted = perm; h.hot_pos = (uint16_t*)(ws + L.hot_pos);
+            h.hot_id = (int32_t*)(ws + L.hot_id); h.bound = (float*)(misc + 32); h.on = (int32_t*)(misc + 33);
+            h.n_hot = 32 * nkey;
+            h.margin = 1.00002f + 2.5e-7f * (float)D;
+            h.hot_bits = (uint32_t*)(ws + L.hot_bits); h.row_bits = (uint32_t*)(ws + L.row_bits);
+            GMR_CHECK_CUDA(cudaMemsetAsync(h.hot_pos, 0xFF, (size_t)I * 2, st));
+            GMR_CHECK_CUDA(cudaMemsetAsync(h.hot_bits, 0, (size_t)(((int64_t)I + 31) / 32 * 4), st));
+            score_head_setup_kernel<<<1, 256, 0, st>>>(h, I, K);
+            GMR_LAUNCH_CHECK();
+            if (mask_rowptr != nullptr) {
+                GMR_CHECK_CUDA(cudaMemsetAsync(h.row_bits, 0, (size_t)L.b_pad * nkey * 4, st));
+                score_head_maskbits_kernel<<<8 * sm_count(), 256, 0, st>>>(mask_rowptr, mask_items, (int64_t)B, h, nullptr);
+                GMR_LAUNCH_CHECK();
+            }
+            const int per_sm = hsmem <= 100 * 1024 ? 2 : 1;
+            const int64_t want = ((int64_t)B + 8 * (32 / nkey) - 1) / (8 * (32 / nkey));
+            const int hgrid = (int)(want < (int64_t)per_sm * sm_count() ? want : (int64_t)per_sm * sm_count());
+            if (nkey == 4) {
+                GMR_CHECK_CUDA(cudaFuncSetAttribute(score_head_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
+                score_head_kernel<4><<<hgrid, 256, hsmem, st>>>(a, h);
+            } else {
+                GMR_CHECK_CUDA(cudaFuncSetAttribute(score_head_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
+                score_head_kernel<8><<<hgrid, 256, hsmem, st>>>(a, h);
+            }
+            GMR_LAUNCH_CHECK();
+        }
+    }
+    if (items_d64)
+        prep_items_d64_kernel<<<(L.i_pad + 8 * wpb - 1) / (8 * wpb), wpb * 32, 0, st>>>(Ei, lde_i, I, L.i_pad, misc, perm, nb, b_h);
+    else
+        prep_items_kernel<<<(L.i_pad + wpb - 1) / wpb, wpb * 32, 0, st>>>(Ei, lde_i, I, L.i_pad, D, misc, perm, nb, b_h);
+    GMR_LAUNCH_CHECK();
+    if (D == 64 && lde_u % 4 == 0 && (uintptr_t)Eu % 16 == 0)
+        prep_users_d64_kernel<<<(L.b_pad + 8 * wpb - 1) / (8 * wpb), wpb * 32, 0, st>>>(
+            Eu, lde_u, users, B, L.b_pad, misc, nb, bias ? misc + 3 : nullptr, a.row_done, a_h, row_const);
+    else
+        prep_users_kernel<<<(L.b_pad + wpb - 1) / wpb, wpb * 32, 0, st>>>(Eu, lde_u, users, B, L.b_pad, D, misc, nb,
+                                                                         bias ? misc + 3 : nullptr, a.row_done, a_h, row_const);
+    GMR_LAUNCH_CHECK();
+    CUtensorMap map_a, map_b;
+    if (!scr_make_map(&map_a, a_h, L.b_pad, D) || !scr_make_map(&map_b, b_h, L.i_pad, D)) {
+        set_error("score_topk_screen: cuTensorMapEncodeTiled unavailable or failed");
+        return GMR_ERR_CUDA;
+    }
     const int n_groups = L.b_pad / kRowsPerCta;
     GMR_CHECK_CUDA(cudaMemsetAsync(a.group_need, 0, (size_t)n_groups * 4, st));
     const int grid = scr_grid(B);

@@ -669,14 +669,15 @@ def last_tc_fallback_rows():
 
 def last_tc_stats():
     """Counters of the most recent ``precision='tc'`` call (all zero unless GMR_SCREEN_STATS is set in the
-    environment): append-path chunks, appended candidates, cheap/exact prunes, re-scored candidates."""
+    environment): append-path chunks, appended candidates, cheap/exact prunes, re-scored candidates, item tiles swept, rows settled by
+    the exact head."""
     if _last_score_call is None or _last_score_call[5] != _lib.GMR_SCORE_TC:
         return {}
     ws, b, i, d, k, _ = _last_score_call
     out = (C.c_uint64 * 8)()
     _lib.check(_lib.load().gmr_score_tc_stats(_ptr(ws), b, i, d, k, out, _stream()), "gmr_score_tc_stats")
     return {"slow_chunks": out[0], "appends": out[1], "cheap_prunes": out[2], "exact_prunes": out[3],
-            "rescored": out[5], "tiles_swept": out[6]}
+            "rescored": out[5], "tiles_swept": out[6], "head_rows": out[7]}
 
 
 def scores_dense(eu, ei, users=None, bias=None):

@@ -358,6 +358,59 @@ def test_score_screen_skewed_norms_early_stop(ops, monkeypatch):
     assert 0 < st["tiles_swept"] < 0.5 * n_groups * full, st
 
 
+@pytest.mark.parametrize("n_items,k,b,with_users", [(30000, 50, 1500, False), (30000, 100, 700, True), (200, 50, 300, False),
+                                                    (128, 20, 260, False), (129, 64, 260, True), (5000, 128, 515, False)])
+def test_score_screen_exact_head(ops, monkeypatch, n_items, k, b, with_users):
+    """The exact head (score_head_kernel): with popularity-skewed norms most rows are settled by the exact scores of
+    the 128 / 256 highest-norm items plus the Cauchy-Schwarz bound of the rest; rows whose history covers the popular
+    items, or whose K-th head score does not beat the bound, continue through the screen.  Ids AND scores must equal
+    the oracle's either way, and switching the head off must not change a bit."""
+    monkeypatch.setenv("GMR_SCREEN_STATS", "1")
+    rng = np.random.default_rng(n_items + k)
+    d = 64
+    scale = np.exp(rng.normal(0.0, 1.5, size=(n_items, 1)))
+    # propagated embeddings share a dominant direction (cosines near 1): only then does |u| |e| bound anything
+    ei = ((1.0 + 0.3 * rng.standard_normal((n_items, d))) * scale).astype(np.float32)
+    n_users = b + 37 if with_users else b
+    eu = (1.0 + 0.3 * rng.standard_normal((n_users, d))).astype(np.float32)
+    eu[3] = 0.0                                            # a zero row: every score ties at 0, cannot finish early
+    eu[5] *= 1e-30                                         # squares underflow: the norm is no bound, the screen takes the row
+    users = rng.permutation(n_users)[:b].astype(np.int64) if with_users else None
+    hot = np.argsort(-scale[:, 0])[:min(400, n_items)]
+    lens = rng.integers(0, min(100, len(hot)), size=b)
+    lens[::40] = min(len(hot), 380)                        # these rows have seen nearly every popular item
+    rows = [np.sort(rng.choice(hot, size=n, replace=False)).astype(np.int32) for n in lens]
+    mrp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    mit = np.concatenate(rows)
+    ids_ref, sc_ref = c_api.score_mask_topk(eu, users, ei, None, mrp, mit, k)
+    args = dict(users=None if users is None else torch.from_numpy(users).cuda(), mask_rowptr=torch.from_numpy(mrp).cuda(),
+                mask_items=torch.from_numpy(mit).cuda(), precision="tc")
+    ids, sc = ops.score_mask_topk(torch.from_numpy(eu).cuda(), torch.from_numpy(ei).cuda(), k, **args)
+    st = ops.last_tc_stats()
+    assert np.array_equal(ids.cpu().numpy(), ids_ref)
+    assert np.array_equal(sc.cpu().numpy(), sc_ref)
+    assert 0 < st["head_rows"] < b, st                     # some rows settled early, the masked-out / zero ones not
+    monkeypatch.setenv("GMR_SCREEN_HEAD", "0")
+    ids0, sc0 = ops.score_mask_topk(torch.from_numpy(eu).cuda(), torch.from_numpy(ei).cuda(), k, **args)
+    assert ops.last_tc_stats()["head_rows"] == 0
+    assert torch.equal(ids0, ids) and torch.equal(sc0, sc)
+
+
+def test_score_screen_head_switches_off_for_flat_norms(ops, monkeypatch):
+    """Flat item norms: no row can beat the outside bound, the head must not run (and nothing changes)."""
+    monkeypatch.setenv("GMR_SCREEN_STATS", "1")
+    rng = np.random.default_rng(2)
+    n_items, d, k, b = 4000, 64, 50, 300
+    ei = rng.standard_normal((n_items, d)).astype(np.float32)
+    ei /= np.linalg.norm(ei, axis=1, keepdims=True)
+    eu = rng.standard_normal((b, d)).astype(np.float32)
+    ids_ref, sc_ref = c_api.score_mask_topk(eu, None, ei, None, None, None, k)
+    ids, sc = ops.score_mask_topk(torch.from_numpy(eu).cuda(), torch.from_numpy(ei).cuda(), k, precision="tc")
+    assert ops.last_tc_stats()["head_rows"] == 0
+    assert np.array_equal(ids.cpu().numpy(), ids_ref)
+    assert np.array_equal(sc.cpu().numpy(), sc_ref)
+
+
 def test_score_screen_heavy_mask(ops):
     """Rows whose train history covers most of the catalogue (fewer than K unmasked items for some): masked
     items must surface with -1e10 exactly like trainer.py:384."""
