@@ -484,6 +484,7 @@ def score_regimes(ctx, args):
             tiles = float(st.get("tiles_swept", 0))
             e.update({"tiles_swept_per_256_users": tiles / n_groups, "tiles_full_sweep": tiles_full,
                       "rescored_per_row": st.get("rescored", 0) / b, "fp32_redo_rows": ops.last_tc_fallback_rows(),
+                      "rows_settled_by_exact_head": int(st.get("head_rows", 0)),
                       "executed_TFLOPs": tiles * 256 * 128 * 2.0 * d / ms / 1e9})
         out[name] = e
     flat = out["flat_norms"]
@@ -494,9 +495,10 @@ def score_regimes(ctx, args):
                 "avg_ms": flat["ms"], "peak_source": peaks["source"] + " bf16 sustained",
                 "note": "executed flops = item tiles actually multiplied x 256 users x 128 items x 2 D, on flat-norm inputs "
                         "where the norm-ordered early stop cannot prune.  On the workload's own embeddings (score_regimes."
-                        "model_embeddings) the sweep stops after tiles_swept_per_256_users of tiles_full_sweep tiles because "
-                        "Cauchy-Schwarz rules the rest out (exact results, checked under 'parity'); that run is bound by the "
-                        "per-row SIMT bookkeeping, not by the tensor pipe."}
+                        "model_embeddings) rows_settled_by_exact_head rows never reach the screen (their exact top K among "
+                        "the highest-norm items beats the Cauchy-Schwarz bound of everything else) and the sweep of the rest "
+                        "stops after tiles_swept_per_256_users of tiles_full_sweep tiles (exact results, checked under "
+                        "'parity'); that run is bound by the per-row CUDA-core selection, not by the tensor pipe."}
     return out, roofline
 
 

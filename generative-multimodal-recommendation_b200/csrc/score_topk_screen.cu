@@ -270,11 +270,7 @@ __global__ void __launch_bounds__(256)
     const int lane = threadIdx.x & 31;
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= n_rows_pad) return;
-    if (r < n_rows && row_done[r]) {
-        // settled by the exact head: its fp16 row is never looked at (a stale row only feeds its own accumulators)
-        if (lane == 0) row_const[r] = RowConst{0.f, 0.f, INFINITY, 0.f};
-        return;
-    }
+    if (r < n_rows && row_done[r]) return;   // settled by the exact head: nothing reads its operand or constants again
     __half* o = out + r * (int64_t)D;
     const float* src = (r < n_rows) ? E + (rows ? rows[r] : r) * lde : nullptr;
     // the row stays in registers between the absmax pass and the conversion (D <= 256: 4 x float2 per lane)
@@ -368,6 +364,9 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
         for (int k = 8; k > 0; k >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, k);
         if (r >= n_rows_pad) continue;
+        // settled by the exact head: nothing reads the row's operand or constants again (its stale fp16 row only
+        // feeds its own, ignored, accumulators)
+        if (r < n_rows && row_done[r]) continue;
         const __half2 lo = __floats2half2_rn(x0, x1), hi = __floats2half2_rn(x2, x3);
         uint2 o;
         o.x = *reinterpret_cast<const uint32_t*>(&lo);
@@ -385,7 +384,6 @@ __global__ void __launch_bounds__(256)
                 rc.ab += 2.4e-7f * rc.sc * __uint_as_float(*biasmax_bits);
             }
             rc.na = na;
-            if (r < n_rows && row_done[r]) rc = RowConst{0.f, 0.f, INFINITY, 0.f};
             row_const[r] = rc;
         }
     }
@@ -570,6 +568,8 @@ struct ScrArgs {
     int32_t vec4;               // Eu / Ei rows are 16-byte aligned
     int32_t first_check;        // tiles swept before the first stop check (phase 0)
     uint8_t* row_done;          // [B_pad] 1: the exact head already wrote the row's top K
+    int32_t* live_rows;         // [B] rows the head left to the screen, in arrival order (valid when *n_live >= 0)
+    int32_t* n_live;            // [1] -1: the head did not run, every row is live
     unsigned long long* stats;  // [kStatSlots] or null
     int32_t debug;              // GMR_TC_DEBUG timing experiments: 1 = drain TMEM only, 2 = filter without appends,
                                 // 3 = no early stop (full sweep; results stay exact)
@@ -686,6 +686,7 @@ struct HeadArgs {
     uint32_t* row_bits;         // [B_pad][n_hot / 32] bit p of row b: head position p is in b's train history
     float* bound;               // [1] unscaled norm of the first item OUTSIDE the head (0: the head is the catalogue)
     int32_t* on;                // [1] 0: no row can finish in the head (flat norms) -- the head kernel returns at once
+    int32_t* n_live;            // [1] ScrArgs::n_live: 0 when the head runs (it appends the rows it leaves), else -1
     int32_t n_hot;
     float margin;               // (1 + rounding slack of the norms and of the fp32 score chains)
 };
@@ -707,20 +708,20 @@ __global__ void __launch_bounds__(256) score_head_setup_kernel(HeadArgs h, int32
         // (a computed norm below ~1e-15 may have lost squares to underflow and is no longer a bound: head off)
         const bool can = (I <= h.n_hot) || (K <= I && out >= 1e-15f && out * h.margin < h.nb_sorted[K - 1]);
         *h.on = can ? 1 : 0;
+        *h.n_live = can ? 0 : -1;
     }
 }
 
-// row_bits of every row from the train-history CSR.  ENTRY-parallel: a warp owns 1,024 consecutive CSR entries whatever
-// rows they belong to (a user with 10^5 interactions costs what 2,000 users with 50 cost; walking the lists row by row
-// inside the head kernel made its longest row -- n_items / 4 entries in the synthetic workloads -- the kernel's duration).
-// The two rows that bracket the chunk come from a binary search of the row pointers; a hit (about one entry in seven
-// passes the hot_bits filter) finds its own row inside that bracket.
+// row_bits of every row from the train-history CSR.  ENTRY-parallel: a warp owns kMaskChunk consecutive CSR entries
+// whatever rows they belong to (a user with 10^5 interactions costs what 2,000 users with 50 cost; walking the lists row
+// by row inside the head kernel made its longest row -- n_items / 4 entries in the synthetic workloads -- the kernel's
+// duration).  The rows that bracket the chunk come from a binary search of the row pointers; the warp then walks the
+// bracket row by row (32 row pointers per load), so no entry ever searches for its row.  About one entry in seven passes
+// the L1-resident hot_bits filter and costs a hot_pos lookup and an atomic OR.
 constexpr int kMaskChunk = 1024;
-__global__ void __launch_bounds__(256)
-    score_head_maskbits_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ items, int64_t B, HeadArgs h,
-                               const uint8_t* __restrict__ unused)
+__global__ void __launch_bounds__(256, 4)
+    score_head_maskbits_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ items, int64_t B, HeadArgs h)
 {
-    (void)unused;
     if (*h.on == 0) return;
     const int lane = threadIdx.x & 31;
     const int64_t base = rowptr[0], end = rowptr[B];
@@ -728,38 +729,37 @@ __global__ void __launch_bounds__(256)
     // the host does not know the number of entries: a fixed grid strides over the chunks
     for (int64_t j0 = base + ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * kMaskChunk; j0 < end;
          j0 += (int64_t)gridDim.x * 8 * kMaskChunk) {
-    const int64_t j1 = (j0 + kMaskChunk < end) ? j0 + kMaskChunk : end;
-    // lane 0: row of entry j0, lane 1: row of entry j1 - 1 (last r with rowptr[r] <= target; empty rows are skipped)
-    int64_t lo = 0;
-    {
-        const int64_t target = lane == 0 ? j0 : j1 - 1;
-        int64_t hi = B;
-        while (hi - lo > 1) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (rowptr[mid] <= target) lo = mid; else hi = mid;
-        }
-    }
-    const int64_t r0 = __shfl_sync(0xffffffffu, lo, 0), r1 = __shfl_sync(0xffffffffu, lo, 1);
-    for (int64_t jb = j0; jb < j1; jb += 128) {
-        int32_t it[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int64_t j = jb + q * 32 + lane;
-            it[q] = j < j1 ? items[j] : -1;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            if (it[q] < 0 || !((h.hot_bits[it[q] >> 5] >> (it[q] & 31)) & 1u)) continue;
-            const int64_t j = jb + q * 32 + lane;
-            const uint32_t p = h.hot_pos[it[q]];
-            int64_t a = r0, b = r1 + 1;   // rowptr[a] <= j < rowptr[b]
-            while (b - a > 1) {
-                const int64_t mid = (a + b) >> 1;
-                if (rowptr[mid] <= j) a = mid; else b = mid;
+        const int64_t j1 = (j0 + kMaskChunk < end) ? j0 + kMaskChunk : end;
+        // lane 0: row of entry j0, lane 1: row of entry j1 - 1 (last r with rowptr[r] <= target; empty rows are skipped)
+        int64_t lo = 0;
+        {
+            const int64_t target = lane == 0 ? j0 : j1 - 1;
+            int64_t hi = B;
+            while (hi - lo > 1) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (rowptr[mid] <= target) lo = mid; else hi = mid;
             }
-            atomicOr(&h.row_bits[a * words + (p >> 5)], 1u << (p & 31));
         }
-    }
+        const int64_t r0 = __shfl_sync(0xffffffffu, lo, 0), r1 = __shfl_sync(0xffffffffu, lo, 1);
+        for (int64_t rb = r0; rb <= r1; rb += 31) {
+            // row pointers rb .. rb + 31 (31 rows per batch: row q needs pointers q and q + 1)
+            const int64_t rq = rb + lane <= B ? rb + lane : B;
+            const int64_t my_rp = rowptr[rq];
+            const int n_rows = (int)((r1 - rb + 1 < 31) ? r1 - rb + 1 : 31);
+            for (int q = 0; q < n_rows; ++q) {
+                int64_t s0 = __shfl_sync(0xffffffffu, my_rp, q), s1 = __shfl_sync(0xffffffffu, my_rp, q + 1);
+                s0 = s0 > j0 ? s0 : j0;
+                s1 = s1 < j1 ? s1 : j1;
+                uint32_t* dst = h.row_bits + (rb + q) * words;
+                for (int64_t j = s0 + lane; j < s1; j += 32) {
+                    const int32_t it = items[j];
+                    if ((h.hot_bits[it >> 5] >> (it & 31)) & 1u) {
+                        const uint32_t p = h.hot_pos[it];
+                        atomicOr(&dst[p >> 5], 1u << (p & 31));
+                    }
+                }
+            }
+        }
     }
 }
 
@@ -968,7 +968,10 @@ __global__ void __launch_bounds__(256, 2) score_head_kernel(ScrArgs a, HeadArgs 
                 }
                 if (sub == 0) n_done += 1;
             }
-            if (sub == 0 && b < a.B) a.row_done[b] = done ? 1 : 0;
+            if (sub == 0 && b < a.B) {
+                a.row_done[b] = done ? 1 : 0;
+                if (!done) a.live_rows[atomicAdd(a.n_live, 1)] = (int32_t)b;
+            }
         }
         __syncwarp();
     }
@@ -1330,10 +1333,13 @@ __global__ void __launch_bounds__(256, (NPL == 8) ? 4 : ((NPL == 16) ? 3 : 2))
 {
     constexpr int CAP = 32 * NPL;
     const int lane = threadIdx.x & 31;
-    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (b >= a.B || a.row_done[b]) return;
+    const int nl = *a.n_live;                      // >= 0: only the rows the exact head left over
+    const int64_t n_work = nl >= 0 ? (int64_t)nl : (int64_t)a.B;
     const int n_itiles = (a.I + kSN - 1) / kSN;
     const int T0 = a.first_check < n_itiles ? a.first_check : n_itiles;
+    for (int64_t idx = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); idx < n_work;
+         idx += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    const int64_t b = nl >= 0 ? (int64_t)a.live_rows[idx] : idx;
     const RowConst rc = a.row_const[b];
     int64_t mlo, mhi;
     row_force_exact(a, b, mlo, mhi);
@@ -1355,6 +1361,7 @@ __global__ void __launch_bounds__(256, (NPL == 8) ? 4 : ((NPL == 16) ? 3 : 2))
         const int need = tiles_needed(a, rc, L, bias_abs_max, T0, n_itiles);
         if (need > T0) atomicMax(&a.group_need[b / kRowsPerCta], need);
     }
+    }
 }
 
 // ---- 3c. finalisation: one warp per row, persistent CTAs ---------------------------------------------
@@ -1371,6 +1378,9 @@ __global__ void __launch_bounds__(256, (NPL == 8) ? 3 : 2)
     float* u_all = fin_smem;                            // [8][D]
     float* e_hot = fin_smem + 8 * a.D;                  // [n_hot][D + 4]
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nl = *a.n_live;                      // >= 0: only the rows the exact head left over
+    const int64_t n_work = nl >= 0 ? (int64_t)nl : (int64_t)a.B;
+    if ((int64_t)blockIdx.x * 8 >= n_work) return;   // no row for this CTA: skip the staging as well
     for (int idx = threadIdx.x; idx < n_hot * (a.D / 4); idx += blockDim.x) {
         const int p = idx / (a.D / 4), j = idx - p * (a.D / 4);
         const int item = a.perm[p];
@@ -1380,8 +1390,8 @@ __global__ void __launch_bounds__(256, (NPL == 8) ? 3 : 2)
     }
     __syncthreads();
     float* u_sm = u_all + w * a.D;
-    for (int64_t b = (int64_t)blockIdx.x * 8 + w; b < a.B; b += (int64_t)gridDim.x * 8) {
-        if (a.row_done[b]) continue;
+    for (int64_t idx = (int64_t)blockIdx.x * 8 + w; idx < n_work; idx += (int64_t)gridDim.x * 8) {
+        const int64_t b = nl >= 0 ? (int64_t)a.live_rows[idx] : idx;
         const RowConst rc = a.row_const[b];
         int64_t mlo, mhi;
         const bool fe = row_force_exact(a, b, mlo, mhi);
@@ -1480,7 +1490,7 @@ static size_t scr_sort_temp_bytes(int32_t I)
 
 struct ScrLayout {
     int64_t a_h, b_h, row_const, nb, perm, nb_raw, ident, sort_tmp, misc, fallback, row_cnt, row_chk, row_L, group_need,
-        slots, simt, hot_pos, hot_id, row_done, hot_bits, row_bits, total;
+        slots, simt, hot_pos, hot_id, row_done, live_rows, hot_bits, row_bits, total;
     int64_t sort_tmp_bytes;
     int32_t b_pad, i_pad;
 };
@@ -1507,7 +1517,7 @@ static ScrLayout scr_layout(int32_t B, int32_t I, int32_t D, int32_t K)
     L.sort_tmp_bytes = (int64_t)scr_sort_temp_bytes(I);
     L.sort_tmp = take(L.sort_tmp_bytes);
     L.misc = take(256);  // u32 [0] item absmax bits, [1] fallback count, [3] bias absmax, [4] group scheduler; u64 stats at +64;
-                         // f32 [32] head bound, i32 [33] head on
+                         // f32 [32] head bound, i32 [33] head on, i32 [34] live-row count (-1: all rows)
     L.fallback = take((int64_t)B * 4);
     L.row_cnt = take((int64_t)L.b_pad * 4);
     L.row_chk = take((int64_t)L.b_pad * 4);
@@ -1518,6 +1528,7 @@ static ScrLayout scr_layout(int32_t B, int32_t I, int32_t D, int32_t K)
     L.hot_pos = take((int64_t)I * 2);
     L.hot_id = take(256 * 4);
     L.row_done = take((int64_t)L.b_pad);
+    L.live_rows = take((int64_t)B * 4);
     L.hot_bits = take(((int64_t)I + 31) / 32 * 4);
     L.row_bits = take((int64_t)L.b_pad * (K <= 64 ? 4 : 8) * 4);
     L.total = off;
@@ -1611,7 +1622,9 @@ int score_topk_screen_launch(const float* Eu, int64_t lde_u, const int64_t* user
     a.stats = getenv("GMR_SCREEN_STATS") ? (unsigned long long*)(ws + L.misc + 64) : nullptr;
     a.debug = getenv("GMR_TC_DEBUG") ? atoi(getenv("GMR_TC_DEBUG")) : 0;
     a.row_done = ws + L.row_done;
+    a.live_rows = (int32_t*)(ws + L.live_rows); a.n_live = (int32_t*)(misc + 34);
     GMR_CHECK_CUDA(cudaMemsetAsync(a.row_done, 0, (size_t)L.b_pad, st));
+    GMR_CHECK_CUDA(cudaMemsetAsync(a.n_live, 0xFF, 4, st));   // -1 unless the head runs
     // exact head over the n_hot highest-norm items (sorted norms are still unscaled here); see the file header
     {
         const int nkey = K <= 64 ? 4 : 8;
@@ -1622,6 +1635,7 @@ int score_topk_screen_launch(const float* Eu, int64_t lde_u, const int64_t* user
             HeadArgs h;
             h.nb_sorted = nb; h.perm_sorted = perm; h.hot_pos = (uint16_t*)(ws + L.hot_pos);
             h.hot_id = (int32_t*)(ws + L.hot_id); h.bound = (float*)(misc + 32); h.on = (int32_t*)(misc + 33);
+            h.n_live = a.n_live;
             h.n_hot = 32 * nkey;
             h.margin = 1.00002f + 2.5e-7f * (float)D;
             h.hot_bits = (uint32_t*)(ws + L.hot_bits); h.row_bits = (uint32_t*)(ws + L.row_bits);
@@ -1631,7 +1645,7 @@ int score_topk_screen_launch(const float* Eu, int64_t lde_u, const int64_t* user
             GMR_LAUNCH_CHECK();
             if (mask_rowptr != nullptr) {
                 GMR_CHECK_CUDA(cudaMemsetAsync(h.row_bits, 0, (size_t)L.b_pad * nkey * 4, st));
-                score_head_maskbits_kernel<<<8 * sm_count(), 256, 0, st>>>(mask_rowptr, mask_items, (int64_t)B, h, nullptr);
+                score_head_maskbits_kernel<<<8 * sm_count(), 256, 0, st>>>(mask_rowptr, mask_items, (int64_t)B, h);
                 GMR_LAUNCH_CHECK();
             }
             const int per_sm = hsmem <= 100 * 1024 ? 2 : 1;
@@ -1680,6 +1694,7 @@ int score_topk_screen_launch(const float* Eu, int64_t lde_u, const int64_t* user
     int fin_ctas_per_sm = (int)((220 * 1024) / (fin_smem > 0 ? fin_smem : 1));
     fin_ctas_per_sm = fin_ctas_per_sm < 1 ? 1 : (fin_ctas_per_sm > 3 ? 3 : fin_ctas_per_sm);
     const int fin_grid = row_blocks < fin_ctas_per_sm * sm_count() ? row_blocks : fin_ctas_per_sm * sm_count();
+    const int chk_grid = row_blocks < 32 * sm_count() ? row_blocks : 32 * sm_count();   // strides over the live rows
     // phase 0 sweep -> checkpoint (mask + first L, per row at full occupancy) -> phase 1 sweep for the groups that
     // still need tiles -> finalisation (exact re-score + sort, per row at full occupancy)
 #define GMR_SCR_LAUNCH(NPL, BIAS)                                                                                  \
@@ -1689,7 +1704,7 @@ int score_topk_screen_launch(const float* Eu, int64_t lde_u, const int64_t* user
         score_screen_sweep_kernel<NPL, BIAS><<<grid, kScrThreads, smem, st>>>(map_a, map_b, a, 0);                 \
         GMR_LAUNCH_CHECK();                                                                                        \
         if (a.debug == 0 || a.debug == 3) {                                                                        \
-            score_screen_checkpoint_kernel<NPL><<<row_blocks, 256, 0, st>>>(a);                                    \
+            score_screen_checkpoint_kernel<NPL><<<chk_grid, 256, 0, st>>>(a);                                      \
             GMR_LAUNCH_CHECK();                                                                                    \
         }                                                                                                          \
         score_screen_sweep_kernel<NPL, BIAS><<<grid, kScrThreads, smem, st>>>(map_a, map_b, a, 1);                 \
