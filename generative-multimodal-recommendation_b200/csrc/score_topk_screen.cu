@@ -715,15 +715,19 @@ __global__ void __launch_bounds__(256) score_head_setup_kernel(HeadArgs h, int32
 // row_bits of every row from the train-history CSR.  ENTRY-parallel: a warp owns kMaskChunk consecutive CSR entries
 // whatever rows they belong to (a user with 10^5 interactions costs what 2,000 users with 50 cost; walking the lists row
 // by row inside the head kernel made its longest row -- n_items / 4 entries in the synthetic workloads -- the kernel's
-// duration).  The rows that bracket the chunk come from a binary search of the row pointers; the warp then walks the
-// bracket row by row (32 row pointers per load), so no entry ever searches for its row.  About one entry in seven passes
-// the L1-resident hot_bits filter and costs a hot_pos lookup and an atomic OR.
+// duration).  The rows that bracket the chunk come from a binary search of the row pointers and their pointers are
+// staged in shared memory; entries are then loaded 128 at a time (coalesced, independent), filtered by the L1-resident
+// hot_bits (about one entry in seven passes), and a hit finds its row by a binary search of the staged pointers.
+// (Walking the bracket row by row instead was latency-bound: two dependent loads per 32 entries, 0.33 ms.)
 constexpr int kMaskChunk = 1024;
+constexpr int kMaskBracket = 160;   // staged row pointers per warp; wider brackets (runs of empty rows) search global memory
 __global__ void __launch_bounds__(256, 4)
     score_head_maskbits_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ items, int64_t B, HeadArgs h)
 {
     if (*h.on == 0) return;
+    __shared__ int64_t rp_all[8][kMaskBracket];
     const int lane = threadIdx.x & 31;
+    int64_t* rp = rp_all[threadIdx.x >> 5];
     const int64_t base = rowptr[0], end = rowptr[B];
     const int words = h.n_hot >> 5;
     // the host does not know the number of entries: a fixed grid strides over the chunks
@@ -741,23 +745,42 @@ __global__ void __launch_bounds__(256, 4)
             }
         }
         const int64_t r0 = __shfl_sync(0xffffffffu, lo, 0), r1 = __shfl_sync(0xffffffffu, lo, 1);
-        for (int64_t rb = r0; rb <= r1; rb += 31) {
-            // row pointers rb .. rb + 31 (31 rows per batch: row q needs pointers q and q + 1)
-            const int64_t rq = rb + lane <= B ? rb + lane : B;
-            const int64_t my_rp = rowptr[rq];
-            const int n_rows = (int)((r1 - rb + 1 < 31) ? r1 - rb + 1 : 31);
-            for (int q = 0; q < n_rows; ++q) {
-                int64_t s0 = __shfl_sync(0xffffffffu, my_rp, q), s1 = __shfl_sync(0xffffffffu, my_rp, q + 1);
-                s0 = s0 > j0 ? s0 : j0;
-                s1 = s1 < j1 ? s1 : j1;
-                uint32_t* dst = h.row_bits + (rb + q) * words;
-                for (int64_t j = s0 + lane; j < s1; j += 32) {
-                    const int32_t it = items[j];
-                    if ((h.hot_bits[it >> 5] >> (it & 31)) & 1u) {
-                        const uint32_t p = h.hot_pos[it];
-                        atomicOr(&dst[p >> 5], 1u << (p & 31));
+        const int n_br = (int)((r1 - r0 + 2 <= kMaskBracket) ? r1 - r0 + 2 : 0);   // pointers r0 .. r1 + 1, 0: not staged
+        __syncwarp();
+        for (int q = lane; q < n_br; q += 32) rp[q] = rowptr[r0 + q];
+        __syncwarp();
+        for (int64_t jb = j0; jb < j1; jb += 128) {
+            int32_t it[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int64_t j = jb + q * 32 + lane;
+                it[q] = j < j1 ? items[j] : -1;
+            }
+            bool hit[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) hit[q] = it[q] >= 0 && ((h.hot_bits[it[q] >> 5] >> (it[q] & 31)) & 1u);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (!hit[q]) continue;
+                const int64_t j = jb + q * 32 + lane;
+                const uint32_t p = h.hot_pos[it[q]];
+                int64_t row;
+                if (n_br > 0) {
+                    int a = 0, b = n_br - 1;        // rp[a] <= j < rp[b]
+                    while (b - a > 1) {
+                        const int mid = (a + b) >> 1;
+                        if (rp[mid] <= j) a = mid; else b = mid;
                     }
+                    row = r0 + a;
+                } else {
+                    int64_t a = r0, b = r1 + 1;     // rowptr[a] <= j < rowptr[b]
+                    while (b - a > 1) {
+                        const int64_t mid = (a + b) >> 1;
+                        if (rowptr[mid] <= j) a = mid; else b = mid;
+                    }
+                    row = a;
                 }
+                atomicOr(&h.row_bits[row * words + (p >> 5)], 1u << (p & 31));
             }
         }
     }
@@ -766,6 +789,9 @@ __global__ void __launch_bounds__(256, 4)
 // Bitonic sort of 16 * P keys owned by a HALF-warp, descending: lane `sub` (0 .. 15 inside its half) holds the elements
 // sub * P .. sub * P + P - 1, so the log2(P) smallest strides of every merge are register-local compare-exchanges (no
 // shuffle, no redundant compare) and only strides >= P cross lanes (xor masks < 16 stay inside the half).
+// (Tried: sorting the 32-bit score words alone -- a third of the network's instructions -- and recovering every
+// element's rank by a binary search of the sorted words in shared memory: 1.46 -> 1.67 ms, the dependent shared-memory
+// probes cost more than the 64-bit compares save.)
 template <int P>
 __device__ __forceinline__ void halfwarp_bitonic_sort_desc(uint64_t (&k)[P], int sub)
 {

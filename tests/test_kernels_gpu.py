@@ -396,6 +396,35 @@ def test_score_screen_exact_head(ops, monkeypatch, n_items, k, b, with_users):
     assert torch.equal(ids0, ids) and torch.equal(sc0, sc)
 
 
+def test_score_screen_exact_head_ties(ops, monkeypatch):
+    """Two of the highest-norm items are identical rows: their scores tie exactly in every row that has not seen one of
+    them, and the head must order the twins by item id like the oracle."""
+    monkeypatch.setenv("GMR_SCREEN_STATS", "1")
+    rng = np.random.default_rng(77)
+    n_items, d, k, b = 20000, 64, 50, 900
+    scale = np.exp(rng.normal(0.0, 1.5, size=(n_items, 1)))
+    ei = ((1.0 + 0.3 * rng.standard_normal((n_items, d))) * scale).astype(np.float32)
+    eu = (1.0 + 0.3 * rng.standard_normal((b, d))).astype(np.float32)
+    hot = np.argsort(-scale[:, 0])
+    ei[hot[4]] = ei[hot[2]]                                 # twins inside every row's top K
+    lens = rng.integers(0, 60, size=b)
+    rows = []
+    for r in range(b):
+        m = set(rng.choice(hot[:300], size=lens[r], replace=False).tolist())
+        if r % 3 == 0:
+            m.add(int(hot[4]))                              # this row has seen one twin: no tie left
+        rows.append(np.sort(np.fromiter(m, dtype=np.int32)))
+    mrp = np.concatenate([[0], np.cumsum([len(x) for x in rows])]).astype(np.int64)
+    mit = np.concatenate(rows).astype(np.int32)
+    ids_ref, sc_ref = c_api.score_mask_topk(eu, None, ei, None, mrp, mit, k)
+    ids, sc = ops.score_mask_topk(torch.from_numpy(eu).cuda(), torch.from_numpy(ei).cuda(), k,
+                                  mask_rowptr=torch.from_numpy(mrp).cuda(), mask_items=torch.from_numpy(mit).cuda(), precision="tc")
+    st = ops.last_tc_stats()
+    assert np.array_equal(ids.cpu().numpy(), ids_ref)
+    assert np.array_equal(sc.cpu().numpy(), sc_ref)
+    assert st["head_rows"] > 0, st
+
+
 def test_score_screen_head_switches_off_for_flat_norms(ops, monkeypatch):
     """Flat item norms: no row can beat the outside bound, the head must not run (and nothing changes)."""
     monkeypatch.setenv("GMR_SCREEN_STATS", "1")
