@@ -201,6 +201,17 @@ class LoaderHead(object):
         return self.eval_len_list
 
 
+def workload_config(wl, label, model_name, shape, n_eval, k, l2_bytes):
+    """The workload a bench line is quoted on -- identical for the GPU arm and the --impl reference arm."""
+    need_flush = shape != "scaled"   # the Amazon shapes are L2-resident (operands of 16-36 MB)
+    cfg = wl.config
+    return {"workload": label, "propagation": PROPAGATION[model_name], "n_users": wl.n_users, "n_items": wl.n_items,
+            "nnz_train": wl.nnz_train, "eval_users": int(n_eval), "topk": int(k), "embedding_size": cfg["embedding_size"],
+            "n_layers": cfg["n_layers"],
+            "l2": ("L2 flushed between timed steps (operands fit the %d MB L2)" % (l2_bytes >> 20)) if need_flush
+            else ("operands exceed the %d MB L2; no flush" % (l2_bytes >> 20))}
+
+
 def run_gpu(args, workload, steps, warmup, main=True):
     """Time one workload.  Returns (json dict on rank 0, context dict)."""
     import torch.distributed as dist
@@ -417,20 +428,19 @@ def run_gpu(args, workload, steps, warmup, main=True):
             "metric": "full_sort_eval_users_per_s", "value": n_eval_total / step_ms * 1e3, "unit": "users/s",
             "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": label, "propagation": PROPAGATION[model_name], "n_users": wl.n_users,
-                       "n_items": wl.n_items, "nnz_train": wl.nnz_train, "eval_users": n_eval_total, "topk": k,
-                       "embedding_size": cfg["embedding_size"], "n_layers": cfg["n_layers"],
-                       "score_precision": args.precision,
-                       "launch": "CUDA graph replay of the whole step" if (use_graph and not graph_state["failed"]) else "eager launches",
-                       "parallelism": ((("column-sharded propagation (each rank owns %d of the %d embedding columns and runs every "
-                                         "SpMM over the whole graph locally; column slices exchanged by NVLink peer stores, "
-                                         "flag barriers in peer memory)" % (cfg["embedding_size"] // world, cfg["embedding_size"]))
-                                        if type(sharded).__name__ == "ColShardedDiffMM" else
-                                        "row-sharded propagation (each rank stores its row block into every peer's replica "
-                                        "over NVLink peer memory)") + " + user-block sharded eval, x%d" % world)
-                       if world > 1 else "single GPU",
-                       "l2": ("L2 flushed between timed steps (operands fit the %d MB L2)" % (l2_bytes >> 20)) if need_flush
-                       else ("operands exceed the %d MB L2; no flush" % (l2_bytes >> 20))},
+            # `config` names the workload only and is the same dict in both arms (--impl reference prints it too);
+            # how THIS arm runs it is under `implementation`
+            "config": workload_config(wl, label, model_name, shape, n_eval_total, k, l2_bytes),
+            "implementation": {
+                "score_precision": args.precision,
+                "launch": "CUDA graph replay of the whole step" if (use_graph and not graph_state["failed"]) else "eager launches",
+                "parallelism": ((("column-sharded propagation (each rank owns %d of the %d embedding columns and runs every "
+                                  "SpMM over the whole graph locally; column slices exchanged by NVLink peer stores, "
+                                  "flag barriers in peer memory)" % (cfg["embedding_size"] // world, cfg["embedding_size"]))
+                                 if type(sharded).__name__ == "ColShardedDiffMM" else
+                                 "row-sharded propagation (each rank stores its row block into every peer's replica "
+                                 "over NVLink peer memory)") + " + user-block sharded eval, x%d" % world)
+                if world > 1 else "single GPU"},
             "propagation_step_ms": prop_ms,
             "spmm_hbm_GBs": kernels[big_spmm]["alg_GBs"] if big_spmm is not None else None,
             "roofline": roofline, "roofline_spmm": roofline_spmm,
@@ -841,9 +851,8 @@ def run_reference(args):
         "n_gpus": world, "steps": args.steps, "steps_run": steps, "warmup": args.warmup, "warmup_run": warm + 1,
         "ms_per_step": base["seconds_per_batch"] * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": label, "propagation": PROPAGATION[model_name], "n_users": wl.n_users,
-                   "n_items": wl.n_items, "nnz_train": wl.nnz_train, "eval_users": wl.n_eval_users, "topk": k,
-                   "embedding_size": wl.config["embedding_size"], "n_layers": wl.config["n_layers"]},
+        "config": workload_config(wl, label, model_name, shape, wl.n_eval_users, k,
+                                  torch.cuda.get_device_properties(dev).L2_cache_size),
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "users/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
