@@ -1236,6 +1236,30 @@ __global__ void __launch_bounds__(kScrThreads, 1)
                         if (f == 0u || a.debug == 2) continue;
                         // ---- slow path (warp-cooperative append; lane = column) ----
                         st_slow += 1;
+                        if (__popc(f) >= 8) {
+                            // ---- dense form (cold thresholds: the first tiles of a sweep, small catalogues) ----
+                            // Most rows of the warp have something to append: the cooperative loop below would run once per
+                            // flagged row (~60 instructions each).  Here every flagged thread appends its own row's columns
+                            // straight from its registers, in column (= sweep) order.  The column's own norm is replaced by
+                            // the chunk's largest (nbc): a looser test only appends a few more candidates.
+                            if (flag) {
+                                const float e = fmaf(rc.ce, nbc, rc.ab);
+                                uint64_t* dst = cta_slots + (int64_t)(warp_row0 + lane) * CAP + cnt;
+                                const int ncol = a.I - cbase;   // columns >= ncol are padding
+                                int n = 0;
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    const float sj = __uint_as_float(v[j]);
+                                    if (j < ncol && sj + e >= L) {
+                                        dst[n] = ((uint64_t)f32_to_ordered(sj) << 32) | (uint32_t)(cbase + j);
+                                        ++n;
+                                    }
+                                }
+                                cnt += n;
+                                st_app += 32ull * (unsigned)n;   // (the cooperative form counts every append on all 32 lanes)
+                            }
+                            __syncwarp();
+                        } else {
                         if (flag) {
 #pragma unroll
                             for (int j8 = 0; j8 < 8; ++j8) {
@@ -1268,6 +1292,7 @@ __global__ void __launch_bounds__(kScrThreads, 1)
                             st_app += n;
                         }
                         __syncwarp();
+                        }
                         unsigned need = __ballot_sync(0xffffffffu, cnt >= TRIG);
                         while (need) {
                             const int l = __ffs(need) - 1;
