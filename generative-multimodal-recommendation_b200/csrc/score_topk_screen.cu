@@ -789,11 +789,11 @@ __global__ void __launch_bounds__(256, 4)
 // Bitonic sort of 16 * P keys owned by a HALF-warp, descending: lane `sub` (0 .. 15 inside its half) holds the elements
 // sub * P .. sub * P + P - 1, so the log2(P) smallest strides of every merge are register-local compare-exchanges (no
 // shuffle, no redundant compare) and only strides >= P cross lanes (xor masks < 16 stay inside the half).
-// (Tried: sorting the 32-bit score words alone -- a third of the network's instructions -- and recovering every
-// element's rank by a binary search of the sorted words in shared memory: 1.46 -> 1.67 ms, the dependent shared-memory
-// probes cost more than the 64-bit compares save.)
-template <int P>
-__device__ __forceinline__ void halfwarp_bitonic_sort_desc(uint64_t (&k)[P], int sub)
+// (Tried first: sorting the 32-bit score words alone and recovering every element's rank by a binary search of the sorted
+// words in shared memory: 1.46 -> 1.67 ms, the dependent shared-memory probes cost more than the 64-bit compares save.
+// The selection below carries the head position INSIDE a 32-bit key instead.)
+template <int P, typename T>
+__device__ __forceinline__ void halfwarp_bitonic_sort_desc(T (&k)[P], int sub)
 {
     constexpr int N = 16 * P;
 #pragma unroll
@@ -805,7 +805,7 @@ __device__ __forceinline__ void halfwarp_bitonic_sort_desc(uint64_t (&k)[P], int
                 const bool take_max = (((sub * P) & size) == 0) == ((sub & ls) == 0);   // size > stride >= P: no r bits
 #pragma unroll
                 for (int r = 0; r < P; ++r) {
-                    const uint64_t other = __shfl_xor_sync(0xffffffffu, k[r], ls);
+                    const T other = __shfl_xor_sync(0xffffffffu, k[r], ls);
                     k[r] = ((k[r] > other) == take_max) ? k[r] : other;
                 }
             } else {
@@ -814,7 +814,7 @@ __device__ __forceinline__ void halfwarp_bitonic_sort_desc(uint64_t (&k)[P], int
                     if ((r & stride) == 0) {
                         const int r2 = r | stride;
                         const bool desc = size < P ? ((r & size) == 0) : ((((sub * P) | r) & size) == 0);
-                        const uint64_t x = k[r], y = k[r2];
+                        const T x = k[r], y = k[r2];
                         const bool sw = (x > y) != desc;   // descending block: larger key first
                         k[r] = sw ? y : x;
                         k[r2] = sw ? x : y;
@@ -846,6 +846,7 @@ __global__ void __launch_bounds__(256, 2) score_head_kernel(ScrArgs a, HeadArgs 
     uint32_t* bm_all = reinterpret_cast<uint32_t*>(sc_all + 8 * R * NH);  // [8 warps][R][NKEY] masked-position bitmaps
     int32_t* ids = reinterpret_cast<int32_t*>(bm_all + 8 * R * NKEY);     // [NH]
     float* na_all = reinterpret_cast<float*>(ids + NH);             // [8 warps][R] row norms (rounded up)
+    uint32_t* so_all = reinterpret_cast<uint32_t*>(na_all + 8 * R); // [8 warps][2][NH] sorted 32-bit keys of the two rows in flight
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int p = threadIdx.x; p < NH; p += blockDim.x) ids[p] = h.hot_id[p];
     for (int idx = threadIdx.x; idx < NH * D; idx += blockDim.x) {
@@ -949,10 +950,68 @@ __global__ void __launch_bounds__(256, 2) score_head_kernel(ScrArgs a, HeadArgs 
         for (int pair = 0; pair < R / 2; ++pair) {
             const int rr = 2 * pair + hw;
             const int64_t b = b0 + rr;
-            uint64_t k[P];
+            // Selection on 32-bit keys: (ordered score word with its PB low bits replaced by PMASK - head position).  A
+            // compare-exchange is then two ALU instructions instead of five (64-bit compare + two selects), and the sorted
+            // key itself says where the element's exact score and item id are.  The truncation can only misorder scores that
+            // agree in their upper 32 - PB bits: if any two NEIGHBOURS among the first K + 1 sorted keys do (a few percent of
+            // the rows; exact ties always do), both rows of the warp take the 64-bit (score, id) network below instead.
+            constexpr uint32_t PB = (NH == 128) ? 7u : 8u, PMASK = (1u << PB) - 1u;
+            const int kth = a.K - 1;   // K <= NH / 2
+            const float na = na_w[rr];
+            const uint32_t mw = bm[rr * NKEY + ((sub * P) >> 5)] >> ((sub * P) & 31);   // P <= 16 bits of one word
+            uint32_t k32[P];
             bool finite = true;
+#pragma unroll
+            for (int r4 = 0; r4 < P / 4; ++r4) {
+                const float4 s4 = *reinterpret_cast<const float4*>(sc_w + rr * NH + sub * P + 4 * r4);
+                const int4 i4 = *reinterpret_cast<const int4*>(ids + sub * P + 4 * r4);
+                const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+                const int iv[4] = {i4.x, i4.y, i4.z, i4.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const bool ok = iv[q] >= 0 && !((mw >> (4 * r4 + q)) & 1u);
+                    finite = finite && (!ok || fabsf(sv[q]) < INFINITY);
+                    // (a finite score's ordered word is >= 2^23: a valid key is never 0)
+                    k32[4 * r4 + q] = ok ? ((f32_to_ordered(sv[q]) & ~PMASK) | (PMASK - (uint32_t)(sub * P + 4 * r4 + q))) : 0u;
+                }
+            }
+            const unsigned fin_bits = __ballot_sync(0xffffffffu, finite);
+            const bool all_finite = ((fin_bits >> (16 * hw)) & 0xFFFFu) == 0xFFFFu;
+            halfwarp_bitonic_sort_desc<P, uint32_t>(k32, sub);
+            uint32_t* so32 = so_all + (size_t)(w * 2 + hw) * NH;
+#pragma unroll
+            for (int r = 0; r < P; ++r) so32[sub * P + r] = k32[r];
+            bool tie = false;
             {
-                const uint32_t mw = bm[rr * NKEY + ((sub * P) >> 5)] >> ((sub * P) & 31);   // P <= 16 bits of one word
+                const uint32_t next_first = __shfl_down_sync(0xffffffffu, k32[0], 1);   // rank (sub + 1) * P
+#pragma unroll
+                for (int r = 0; r < P; ++r) {
+                    const uint32_t nxt = (r + 1 < P) ? k32[r + 1] : next_first;
+                    tie = tie || (sub * P + r <= kth && k32[r] != 0u && ((k32[r] ^ nxt) >> PB) == 0u);   // ranks (j, j + 1), j < K
+                }
+            }
+            const bool any_tie = __ballot_sync(0xffffffffu, tie) != 0u;   // warp-uniform: both rows switch together
+            __syncwarp();
+            bool done;
+            if (!any_tie) {
+                const uint32_t kk = so32[kth];   // 0: fewer than K unmasked head items
+                const float s_k = sc_w[rr * NH + (PMASK - (kk & PMASK))];   // the K-th best EXACT score
+                // every item outside the head scores (as computed in fp32) at most |u| * bound * margin
+                done = b < a.B && ((cand_bits >> rr) & 1u) && all_finite && kk != 0u && na < INFINITY &&
+                       (whole || na * bound * h.margin < s_k);
+                if (done) {
+#pragma unroll
+                    for (int r = 0; r < P; ++r) {
+                        const int j = sub * P + r;
+                        if (j < a.K) {
+                            const uint32_t pos = PMASK - (k32[r] & PMASK);
+                            a.out_ids[b * a.K + j] = ids[pos];
+                            if (a.out_scores) a.out_scores[b * a.K + j] = sc_w[rr * NH + pos] + 0.0f;   // (-0 -> +0 like key_score)
+                        }
+                    }
+                }
+            } else {
+                uint64_t k[P];
 #pragma unroll
                 for (int r4 = 0; r4 < P / 4; ++r4) {
                     const float4 s4 = *reinterpret_cast<const float4*>(sc_w + rr * NH + sub * P + 4 * r4);
@@ -962,38 +1021,32 @@ __global__ void __launch_bounds__(256, 2) score_head_kernel(ScrArgs a, HeadArgs 
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const bool ok = iv[q] >= 0 && !((mw >> (4 * r4 + q)) & 1u);
-                        finite = finite && (!ok || fabsf(sv[q]) < INFINITY);
                         k[4 * r4 + q] = ok ? make_key(sv[q], iv[q]) : 0ull;
                     }
                 }
-            }
-            const unsigned fin_bits = __ballot_sync(0xffffffffu, finite);
-            const bool all_finite = ((fin_bits >> (16 * hw)) & 0xFFFFu) == 0xFFFFu;
-            halfwarp_bitonic_sort_desc<P>(k, sub);
-            const int kth = a.K - 1;   // K <= NH / 2
-            // the K-th key's score word through shared memory (a register array indexed by kth % P would live in local
-            // memory); 0 = fewer than K unmasked head items (no finite score orders to 0)
-            __syncwarp();
-            uint32_t* so = reinterpret_cast<uint32_t*>(sc_w + rr * NH);
+                halfwarp_bitonic_sort_desc<P, uint64_t>(k, sub);
+                // the K-th key's score word through shared memory (a register array indexed by kth % P would live in local
+                // memory); 0 = fewer than K unmasked head items (no finite score orders to 0)
+                __syncwarp();
 #pragma unroll
-            for (int r = 0; r < P; ++r) so[sub * P + r] = (uint32_t)(k[r] >> 32);
-            __syncwarp();
-            const uint32_t kk = so[kth];
-            // every item outside the head scores (as computed in fp32) at most |u| * bound * margin
-            const float na = na_w[rr];
-            const bool done = b < a.B && ((cand_bits >> rr) & 1u) && all_finite && kk != 0u && na < INFINITY &&
-                              (whole || na * bound * h.margin < ordered_to_f32(kk));
-            if (done) {
+                for (int r = 0; r < P; ++r) so32[sub * P + r] = (uint32_t)(k[r] >> 32);
+                __syncwarp();
+                const uint32_t kk = so32[kth];
+                done = b < a.B && ((cand_bits >> rr) & 1u) && all_finite && kk != 0u && na < INFINITY &&
+                       (whole || na * bound * h.margin < ordered_to_f32(kk));
+                if (done) {
 #pragma unroll
-                for (int r = 0; r < P; ++r) {
-                    const int j = sub * P + r;
-                    if (j < a.K) {
-                        a.out_ids[b * a.K + j] = key_id(k[r]);
-                        if (a.out_scores) a.out_scores[b * a.K + j] = key_score(k[r]);
+                    for (int r = 0; r < P; ++r) {
+                        const int j = sub * P + r;
+                        if (j < a.K) {
+                            a.out_ids[b * a.K + j] = key_id(k[r]);
+                            if (a.out_scores) a.out_scores[b * a.K + j] = key_score(k[r]);
+                        }
                     }
                 }
-                if (sub == 0) n_done += 1;
+                if (a.stats != nullptr && lane == 0) atomicAdd(&a.stats[4], 1ull);   // pairs that needed the 64-bit network
             }
+            if (done && sub == 0) n_done += 1;
             if (sub == 0 && b < a.B) {
                 a.row_done[b] = done ? 1 : 0;
                 if (!done) a.live_rows[atomicAdd(a.n_live, 1)] = (int32_t)b;
@@ -1008,7 +1061,7 @@ static size_t head_smem_bytes(int nkey, int32_t D)
 {
     const int nh = 32 * nkey, r = 32 / nkey;
     return (size_t)nh * (D + 4) * 4 + (size_t)8 * r * D * 4 + (size_t)8 * r * nh * 4 + (size_t)8 * r * nkey * 4 + (size_t)nh * 4 +
-           (size_t)8 * r * 4;
+           (size_t)8 * r * 4 + (size_t)8 * 2 * nh * 4;
 }
 
 // ---- 3a. the sweep kernel (TMA + tcgen05 + screening epilogue) ----------------------------------------
@@ -1599,7 +1652,8 @@ int score_screen_fallback_count(const void* workspace, int32_t B, int32_t I, int
 }
 
 // diagnostics of the last call with GMR_SCREEN_STATS=1: [0] slow-path chunks, [1] appends, [2] pool prunes,
-// [3] exact prunes, [5] exactly re-scored candidates, [6] item tiles swept (summed over 256-user groups),
+// [3] exact prunes, [4] row pairs of the exact head that needed the 64-bit network, [5] exactly re-scored candidates,
+// [6] item tiles swept (summed over 256-user groups),
 // [7] rows settled by the exact head
 int score_screen_stats(const void* workspace, int32_t B, int32_t I, int32_t D, int32_t K, uint64_t* stats_host,
                        cudaStream_t st)

@@ -677,7 +677,7 @@ def last_tc_stats():
     out = (C.c_uint64 * 8)()
     _lib.check(_lib.load().gmr_score_tc_stats(_ptr(ws), b, i, d, k, out, _stream()), "gmr_score_tc_stats")
     return {"slow_chunks": out[0], "appends": out[1], "cheap_prunes": out[2], "exact_prunes": out[3],
-            "rescored": out[5], "tiles_swept": out[6], "head_rows": out[7]}
+            "head_pairs_64bit": out[4], "rescored": out[5], "tiles_swept": out[6], "head_rows": out[7]}
 
 
 def scores_dense(eu, ei, users=None, bias=None):

@@ -398,7 +398,8 @@ def test_score_screen_exact_head(ops, monkeypatch, n_items, k, b, with_users):
 
 def test_score_screen_exact_head_ties(ops, monkeypatch):
     """Two of the highest-norm items are identical rows: their scores tie exactly in every row that has not seen one of
-    them, and the head must order the twins by item id like the oracle."""
+    them, and the head must order the twins by item id like the oracle (its 32-bit selection cannot: such rows switch to
+    the 64-bit (score, id) network)."""
     monkeypatch.setenv("GMR_SCREEN_STATS", "1")
     rng = np.random.default_rng(77)
     n_items, d, k, b = 20000, 64, 50, 900
@@ -423,6 +424,7 @@ def test_score_screen_exact_head_ties(ops, monkeypatch):
     assert np.array_equal(ids.cpu().numpy(), ids_ref)
     assert np.array_equal(sc.cpu().numpy(), sc_ref)
     assert st["head_rows"] > 0, st
+    assert st["head_pairs_64bit"] > 0, st                   # the 32-bit selection saw the tie and handed the rows over
 
 
 def test_score_screen_head_switches_off_for_flat_norms(ops, monkeypatch):
