@@ -4,7 +4,8 @@
 // the numpy kernels of GenMMRec/src/utils/metrics.py:12-105 (mean over users taken by the caller,
 // topk_evaluator.py:299-313).  Integer work (hits, cumulative hit counts) is bit-exact; the fp64
 // sums are accumulated in a FIXED order (warp tree -> warps in order -> blocks strided/tree), so the
-// result is run-to-run deterministic and within a few ulp of numpy's pairwise sum.
+// result is run-to-run deterministic and within a few ulp of numpy's pairwise sum.  The warp tree is evaluated
+// column-wise through a shared-memory tile (same additions in the same order as the shuffle butterfly it replaced).
 #include <cmath>
 
 #include <mutex>
@@ -15,16 +16,11 @@
 namespace gmr {
 
 constexpr int kMU = 128;  // users per CTA (one thread each)
-constexpr int kKC = 32;   // top-K positions staged per pass
+constexpr int kKC = 16;   // top-K positions staged per pass
+constexpr int kKS = 4;    // positions whose per-user values are reduced together (16 columns = 4 metrics x 4 positions)
+constexpr int kVP = 4 * kKS + 1;   // row pitch of the value tile in doubles (odd: conflict-free 64-bit stores)
 
 __constant__ double c_discount[GMR_MAX_TOPK];  // 1 / log2(k + 2)
-
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-    return v;
-}
 
 // block_sums layout: [4 * K][n_blocks]  (metric-major, then position, then block)
 __global__ void __launch_bounds__(kMU)
@@ -34,6 +30,7 @@ __global__ void __launch_bounds__(kMU)
 {
     __shared__ int32_t tile[kMU][kKC + 1];
     __shared__ double wsum[kMU / 32][4][kKC];
+    __shared__ double vals[kMU][kVP];
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int64_t u0 = (int64_t)blockIdx.x * kMU;
@@ -62,46 +59,64 @@ __global__ void __launch_bounds__(kMU)
             tile[r][k] = (u0 + r < U) ? topk[(u0 + r) * K + k0 + k] : -1;
         }
         __syncthreads();
-        for (int k = 0; k < kc; ++k) {
-            const int pos = k0 + k;
-            int h = 0;
-            if (valid) h = sorted_contains(gt_items, lo, hi, tile[t][k]) ? 1 : 0;
-            tile[t][k] = h;
-            double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-            if (valid) {
-                // fp64 divides are the cost of this kernel (5 per user and position when written literally): the hit
-                // count c changes on a hit only, the ideal DCG only while pos < lim, so quotients are refreshed when
-                // their operands change and reused otherwise -- same expressions, same results
-                const double disc = c_discount[pos];
-                if (h) {
-                    c += 1.0;
-                    dcg += disc;
-                    sp += c / (double)(pos + 1);
-                    q_recall = c / n;
+        for (int ks = 0; ks < kc; ks += kKS) {
+#pragma unroll
+            for (int kk = 0; kk < kKS; ++kk) {
+                const int k = ks + kk;
+                double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+                if (k < kc) {
+                    const int pos = k0 + k;
+                    int h = 0;
+                    if (valid) h = sorted_contains(gt_items, lo, hi, tile[t][k]) ? 1 : 0;
+                    tile[t][k] = h;
+                    if (valid) {
+                        // fp64 divides are the cost of the arithmetic (5 per user and position when written literally):
+                        // the hit count c changes on a hit only, the ideal DCG only while pos < lim, so quotients are
+                        // refreshed when their operands change and reused otherwise -- same expressions, same results
+                        const double disc = c_discount[pos];
+                        if (h) {
+                            c += 1.0;
+                            dcg += disc;
+                            sp += c / (double)(pos + 1);
+                            q_recall = c / n;
+                        }
+                        if (pos < lim) {
+                            idcg += disc;
+                            q_ndcg = dcg / idcg;
+                            q_map = sp / (double)(pos + 1);
+                        } else if (h) {
+                            q_ndcg = dcg / idcg;
+                            q_map = sp / (double)lim;
+                        }
+                        v0 = q_recall;
+                        v1 = q_ndcg;
+                        v2 = (c != 0.0) ? c / (double)(pos + 1) : 0.0;
+                        v3 = q_map;
+                    }
                 }
-                if (pos < lim) {
-                    idcg += disc;
-                    q_ndcg = dcg / idcg;
-                    q_map = sp / (double)(pos + 1);
-                } else if (h) {
-                    q_ndcg = dcg / idcg;
-                    q_map = sp / (double)lim;
-                }
-                v0 = q_recall;
-                v1 = q_ndcg;
-                v2 = (c != 0.0) ? c / (double)(pos + 1) : 0.0;
-                v3 = q_map;
+                vals[t][0 * kKS + kk] = v0;
+                vals[t][1 * kKS + kk] = v1;
+                vals[t][2 * kKS + kk] = v2;
+                vals[t][3 * kKS + kk] = v3;
             }
-            v0 = warp_sum(v0);
-            v1 = warp_sum(v1);
-            v2 = warp_sum(v2);
-            v3 = warp_sum(v3);
-            if (lane == 0) {
-                wsum[warp][0][k] = v0;
-                wsum[warp][1][k] = v1;
-                wsum[warp][2][k] = v2;
-                wsum[warp][3][k] = v3;
+            __syncwarp();
+            {
+                // Column sums over this warp's 32 users in the order of the xor-butterfly (16, 8, 4, 2, 1) the kernel
+                // used to run with shuffles -- 40 SHFL + 20 DADD per warp and position -- so the sums keep their bits:
+                // lane = (h, column) adds the users of parity h as that tree does, the two parities meet in one shuffle.
+                const int col = lane & 15, h = lane >> 4;
+                const double* vw = &vals[warp * 32][col];
+                double a8[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a8[i] = vw[(h + 2 * i) * kVP] + vw[(h + 2 * i + 16) * kVP];   // a_j, j = h + 2 i
+                const double b0 = a8[0] + a8[4], b1 = a8[1] + a8[5], b2 = a8[2] + a8[6], b3 = a8[3] + a8[7];   // b_j = a_j + a_{j+8}
+                const double c0 = b0 + b2, c1 = b1 + b3;                                                   // c_j = b_j + b_{j+4}
+                double dsum = c0 + c1;                                                                     // d_h = c_h + c_{h+2}
+                dsum += __shfl_xor_sync(0xffffffffu, dsum, 16);                                            // d_0 + d_1
+                const int m = col / kKS, kk = col - m * kKS;
+                if (h == 0 && ks + kk < kc) wsum[warp][m][ks + kk] = dsum;
             }
+            __syncwarp();
         }
         __syncthreads();
         if (hit != nullptr) {

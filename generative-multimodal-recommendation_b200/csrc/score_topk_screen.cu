@@ -725,9 +725,9 @@ __global__ void __launch_bounds__(256, 4)
     score_head_maskbits_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ items, int64_t B, HeadArgs h)
 {
     if (*h.on == 0) return;
-    __shared__ int64_t rp_all[8][kMaskBracket];
+    __shared__ int32_t rp_all[8][kMaskBracket];   // row pointers of the bracket as offsets from the chunk start (clamped)
     const int lane = threadIdx.x & 31;
-    int64_t* rp = rp_all[threadIdx.x >> 5];
+    int32_t* rp = rp_all[threadIdx.x >> 5];
     const int64_t base = rowptr[0], end = rowptr[B];
     const int words = h.n_hot >> 5;
     // the host does not know the number of entries: a fixed grid strides over the chunks
@@ -747,7 +747,10 @@ __global__ void __launch_bounds__(256, 4)
         const int64_t r0 = __shfl_sync(0xffffffffu, lo, 0), r1 = __shfl_sync(0xffffffffu, lo, 1);
         const int n_br = (int)((r1 - r0 + 2 <= kMaskBracket) ? r1 - r0 + 2 : 0);   // pointers r0 .. r1 + 1, 0: not staged
         __syncwarp();
-        for (int q = lane; q < n_br; q += 32) rp[q] = rowptr[r0 + q];
+        for (int q = lane; q < n_br; q += 32) {
+            const int64_t off = rowptr[r0 + q] - j0;   // <= 0 for rows that begin before the chunk, > chunk for rows after it
+            rp[q] = (int32_t)(off < -1 ? -1 : (off > 2 * kMaskChunk ? 2 * kMaskChunk : off));
+        }
         __syncwarp();
         for (int64_t jb = j0; jb < j1; jb += 128) {
             int32_t it[4];
@@ -766,10 +769,11 @@ __global__ void __launch_bounds__(256, 4)
                 const uint32_t p = h.hot_pos[it[q]];
                 int64_t row;
                 if (n_br > 0) {
-                    int a = 0, b = n_br - 1;        // rp[a] <= j < rp[b]
+                    const int jj = (int)(j - j0);   // 0 .. kMaskChunk - 1
+                    int a = 0, b = n_br - 1;        // rp[a] <= jj < rp[b]
                     while (b - a > 1) {
                         const int mid = (a + b) >> 1;
-                        if (rp[mid] <= j) a = mid; else b = mid;
+                        if (rp[mid] <= jj) a = mid; else b = mid;
                     }
                     row = r0 + a;
                 } else {
