@@ -358,16 +358,18 @@ def test_score_screen_skewed_norms_early_stop(ops, monkeypatch):
     assert 0 < st["tiles_swept"] < 0.5 * n_groups * full, st
 
 
-@pytest.mark.parametrize("n_items,k,b,with_users", [(30000, 50, 1500, False), (30000, 100, 700, True), (200, 50, 300, False),
-                                                    (128, 20, 260, False), (129, 64, 260, True), (5000, 128, 515, False)])
-def test_score_screen_exact_head(ops, monkeypatch, n_items, k, b, with_users):
+@pytest.mark.parametrize("n_items,k,b,with_users,d", [(30000, 50, 1500, False, 64), (30000, 100, 700, True, 64),
+                                                      (200, 50, 300, False, 64), (128, 20, 260, False, 64),
+                                                      (129, 64, 260, True, 64), (5000, 128, 515, False, 64),
+                                                      (20000, 50, 600, True, 128), (20000, 80, 300, False, 128),
+                                                      (20000, 50, 600, False, 192)])
+def test_score_screen_exact_head(ops, monkeypatch, n_items, k, b, with_users, d):
     """The exact head (score_head_kernel): with popularity-skewed norms most rows are settled by the exact scores of
     the 128 / 256 highest-norm items plus the Cauchy-Schwarz bound of the rest; rows whose history covers the popular
     items, or whose K-th head score does not beat the bound, continue through the screen.  Ids AND scores must equal
     the oracle's either way, and switching the head off must not change a bit."""
     monkeypatch.setenv("GMR_SCREEN_STATS", "1")
-    rng = np.random.default_rng(n_items + k)
-    d = 64
+    rng = np.random.default_rng(n_items + k + d)
     scale = np.exp(rng.normal(0.0, 1.5, size=(n_items, 1)))
     # propagated embeddings share a dominant direction (cosines near 1): only then does |u| |e| bound anything
     ei = ((1.0 + 0.3 * rng.standard_normal((n_items, d))) * scale).astype(np.float32)
