@@ -398,6 +398,23 @@ def test_score_screen_exact_head(ops, monkeypatch, n_items, k, b, with_users, d)
     assert torch.equal(ids0, ids) and torch.equal(sc0, sc)
 
 
+def test_score_screen_exact_head_without_mask(ops, monkeypatch):
+    """No train-history mask at all (mask_rowptr = NULL): the head's bitmap pass is skipped and every row is a candidate."""
+    monkeypatch.setenv("GMR_SCREEN_STATS", "1")
+    rng = np.random.default_rng(5)
+    n_items, d, k, b = 12000, 64, 50, 700
+    scale = np.exp(rng.normal(0.0, 1.5, size=(n_items, 1)))
+    ei = ((1.0 + 0.3 * rng.standard_normal((n_items, d))) * scale).astype(np.float32)
+    eu = (1.0 + 0.3 * rng.standard_normal((b, d))).astype(np.float32)
+    eu[7] = -eu[7]                                          # every score negative: the bound can never be beaten
+    ids_ref, sc_ref = c_api.score_mask_topk(eu, None, ei, None, None, None, k)
+    ids, sc = ops.score_mask_topk(torch.from_numpy(eu).cuda(), torch.from_numpy(ei).cuda(), k, precision="tc")
+    st = ops.last_tc_stats()
+    assert np.array_equal(ids.cpu().numpy(), ids_ref)
+    assert np.array_equal(sc.cpu().numpy(), sc_ref)
+    assert 0 < st["head_rows"] < b, st
+
+
 def test_score_screen_exact_head_ties(ops, monkeypatch):
     """Two of the highest-norm items are identical rows: their scores tie exactly in every row that has not seen one of
     them, and the head must order the twins by item id like the oracle (its 32-bit selection cannot: such rows switch to
